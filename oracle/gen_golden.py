@@ -1,0 +1,133 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE.  Run in the BUILD container only (needs /root/reference).
+
+Pins the oracle and writes the committed fixtures under tests/golden/:
+
+1. tflow_n{N}.npz -- the UNMODIFIED reference ``TFlow`` (imported from /root/reference over the oracle
+   shims) is loaded with ``oracle.tflow_port.random_init_state_dict(seed)`` and run on a seeded synthetic
+   frame pair; the oracle port must reproduce its four flows bit-for-bit and its FPS indices exactly, or
+   this script aborts.  Stored: inputs, reference outputs, seeds.
+2. solve_rt.npz -- the reference's own ``slove_RT_by_SVD`` source text (scripts/PointCloudOdometry.py:15-33)
+   is exec'd verbatim and compared with oracle.frontend.solve_rt_svd; stored with inputs.
+3. point_ops.npz -- small clouds with exact duplicates: FPS / kNN / 3-NN / ball-query results of the C and
+   the torch restatements (which must agree).  The extension is absent from the reference, so these pin
+   the written tie-breaking spec only ("parity unpinned").
+4. masker.npz -- oracle.frontend.masker_spec on a synthetic frame with gt flow (+ noise), noSeg and Seg.
+
+Usage:  python -m oracle.gen_golden
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import frontend, point_ops, tflow_port  # noqa: E402
+from oracle.ref_harness import import_reference_tflow  # noqa: E402
+from ssf_slam_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def gen_tflow(n_points, data_seed, weight_seed=0):
+    TFlow = import_reference_tflow()
+    sd = tflow_port.random_init_state_dict(weight_seed)
+    net = TFlow().eval()
+    net.load_state_dict(sd, strict=True)
+    item = synth.make_pair(data_seed, n_points)
+    pc1 = torch.from_numpy(item["pos1"].T.copy()).unsqueeze(0)
+    pc2 = torch.from_numpy(item["pos2"].T.copy()).unsqueeze(0)
+    with torch.no_grad():
+        flows, fps = net(pc1, pc2)
+    pflows, pfps = tflow_port.tflow_forward(sd, pc1, pc2)
+    for a, b in zip(flows, pflows):
+        assert torch.equal(a, b), "oracle port deviates from the reference"
+    for a, b in zip(fps, pfps):
+        assert torch.equal(a, b), "oracle port FPS deviates from the reference"
+    np.savez_compressed(os.path.join(OUT, "tflow_n%d.npz" % n_points), pos1=item["pos1"], pos2=item["pos2"],
+                        flow0=flows[0][0].numpy(), flow1=flows[1][0].numpy(), flow2=flows[2][0].numpy(),
+                        flow3=flows[3][0].numpy(), fps1=fps[0][0].numpy(), fps2=fps[1][0].numpy(), fps3=fps[2][0].numpy(),
+                        weight_seed=weight_seed, data_seed=data_seed)
+    print("tflow_n%d: reference == port (bit-exact); |flow|max %.4f" % (n_points, float(flows[0].abs().max())))
+
+
+def _reference_solve_rt():
+    path = "/root/reference/scripts/PointCloudOdometry.py"
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "slove_RT_by_SVD"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module([fn], []), path, "exec"), ns)
+    return ns["slove_RT_by_SVD"]
+
+
+def gen_solve_rt():
+    ref = _reference_solve_rt()
+    rng = np.random.default_rng(11)
+    src = rng.uniform(-50, 50, (500, 3))
+    yaw, pitch = 0.03, -0.01
+    Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    Ry = np.array([[np.cos(pitch), 0, np.sin(pitch)], [0, 1, 0], [-np.sin(pitch), 0, np.cos(pitch)]])
+    dst = src @ (Rz @ Ry).T + np.array([1.2, -0.1, 0.02]) + 0.01 * rng.standard_normal((500, 3))
+    R, t = ref(src, dst)
+    R2, t2 = frontend.solve_rt_svd(src, dst)
+    assert np.array_equal(R, R2) and np.array_equal(t, t2), "solve_rt_svd deviates from the reference"
+    np.savez_compressed(os.path.join(OUT, "solve_rt.npz"), src=src, dst=dst, R=R, t=t)
+    print("solve_rt: reference == oracle (bit-exact)")
+
+
+def gen_point_ops():
+    rng = np.random.default_rng(5)
+    B, N = 2, 1500
+    xyz = rng.uniform(-30, 30, (B, N, 3)).astype(np.float32)
+    xyz[:, 300:500] = xyz[:, 0:200]  # exact duplicates -> exact distance ties
+    xyz[:, 700:720] = xyz[:, 0:1]    # a 21-fold duplicate (more copies than k)
+    query = np.concatenate([xyz[:, ::5], rng.uniform(-30, 30, (B, 100, 3)).astype(np.float32)], 1)
+    out = dict(xyz=xyz, query=query)
+    saved = point_ops.USE_C
+    res = {}
+    for use_c in (True, False):
+        point_ops.USE_C = use_c
+        x, q = torch.from_numpy(xyz), torch.from_numpy(query)
+        res[use_c] = dict(
+            fps=point_ops.furthest_point_sample(x, 256).numpy(),
+            knn16=point_ops.knn(16, q, x), knn7=point_ops.knn(7, q, x), nn3=point_ops.three_nn(q, x))
+    point_ops.USE_C = saved
+    assert np.array_equal(res[True]["fps"], res[False]["fps"])
+    for k in ("knn16", "knn7", "nn3"):
+        assert torch.equal(res[True][k][0], res[False][k][0]) and torch.equal(res[True][k][1], res[False][k][1]), k
+    out["fps256"] = res[True]["fps"]
+    for k in ("knn16", "knn7", "nn3"):
+        out[k + "_dist"] = res[True][k][0].numpy()
+        out[k + "_idx"] = res[True][k][1].numpy()
+    for r in (0.5, 2.0, 4.0):
+        bi, bc = point_ops.ball_query(r, 16, torch.from_numpy(xyz), torch.from_numpy(query))
+        ci, cc = point_ops.c_ball_query(r, 16, xyz, query)
+        assert np.array_equal(bi.numpy(), ci) and np.array_equal(bc.numpy(), cc)
+        out["ball_r%g_idx" % r] = ci
+        out["ball_r%g_cnt" % r] = cc
+    np.savez_compressed(os.path.join(OUT, "point_ops.npz"), **out)
+    print("point_ops: C == torch restatement")
+
+
+def gen_masker():
+    item = synth.make_pair(2000, 8192)
+    rng = np.random.default_rng(3)
+    flow = (item["gt"] + 0.02 * rng.standard_normal(item["gt"].shape)).astype(np.float32)
+    a = frontend.masker_spec(item["pos1"], flow, 0.10)
+    b = frontend.masker_spec(item["pos1"], flow, 0.10, sem=item["sem"], inst=item["inst"], movable=synth.MOVABLE_CLASSES)
+    np.savez_compressed(os.path.join(OUT, "masker.npz"), pos1=item["pos1"], flow=flow, sem=item["sem"], inst=item["inst"],
+                        s_fg_mask=item["s_fg_mask"], mask_noseg=a["mask"], odom_noseg=a["odom"], mask_seg=b["mask"],
+                        odom_seg=b["odom"], R0_noseg=a["R0"], t0_noseg=a["t0"])
+    print("masker: noSeg dyn %d, Seg dyn %d, gt fg %d" % (a["mask"].sum(), b["mask"].sum(), item["s_fg_mask"].sum()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_solve_rt()
+    gen_point_ops()
+    gen_masker()
+    gen_tflow(2048, data_seed=42)
+    gen_tflow(8192, data_seed=0)

@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- scene-flow frame-pairs/s @N=8192 (BASELINE.json metric) for the B200-native front end.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A *step* is one pass of the hot path (scene-flow network + dynamic mask + ego-motion) over one batch of B synthetic
+CARLA-shaped frame pairs of a 200-frame sequence (BASELINE.json configs[1]; weak scaling: every rank processes its own
+sequences, configs[3]).  `value` = frame pairs per second over all ranks with inputs resident in HBM; `e2e` = the same
+through `SceneFlowFrontEnd.process` from pinned HOST buffers (H2D + kernels + D2H of masks and poses).
+`--impl reference` times the reference pipeline's CPU implementation (the oracle port of the reference's Python:
+unmodified-reference-pinned TFlow port + reference GMM masker + slove_RT_by_SVD) on the host cores.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scene-flow frame-pairs/s @N=8192"
+UNIT = "frame-pairs/s"
+POOL = 16  # distinct synthetic frame pairs generated on the host; batches cycle through them
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--npoints", type=int, default=8192)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="frame pairs in the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tensor=1590.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_pipeline_seconds(pool, n_pairs, sd):
+    """Reference pipeline on the host: oracle TFlow port (pinned bit-exact to the unmodified reference) + the
+    reference noSeg masker (sklearn GMM, majority = background) + slove_RT_by_SVD; returns seconds per frame pair."""
+    import torch
+    from oracle import frontend as ofe
+    from oracle import tflow_port as tp
+    torch.set_num_threads(os.cpu_count())
+    times = []
+    for i in range(n_pairs):
+        it = pool[i % len(pool)]
+        t0 = time.perf_counter()
+        pc1 = torch.from_numpy(it["pos1"].T.copy()).unsqueeze(0)
+        pc2 = torch.from_numpy(it["pos2"].T.copy()).unsqueeze(0)
+        flows, _ = tp.tflow_forward(sd, pc1, pc2)
+        flow = flows[0][0].numpy().T.copy()
+        bg = ofe.gmm_background(it["pos1"], flow, random_state=0)
+        R, t = ofe.reference_pose(it["pos1"], flow, bg)
+        ofe.odom_message(R, t)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch
+    from ssf_slam_b200 import synth
+    from ssf_slam_b200.weights import random_init_state_dict
+    pool = synth.make_sequence(1000, 2, args.npoints)
+    sd = random_init_state_dict(0)
+    cpu_pipeline_seconds(pool, max(1, min(args.warmup, 1)), sd)  # warm-up (one pair; a CPU pair takes seconds)
+    t = cpu_pipeline_seconds(pool, args.steps, sd)
+    total = float(sum(t))
+    v = args.steps / total
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 200-frame synthetic sequence, N=%d, noSeg_ActiveSceneFlow pipeline; "
+                                   "one frame pair per step on host cores" % args.npoints},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d frame pairs: oracle TFlow port (bit-exact to the unmodified reference on CPU, "
+                                       "C/OpenMP FPS+kNN) + sklearn GMM mask + slove_RT_by_SVD" % args.steps},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def cost_volume_flops(n1, m):
+    """2*MAC of one ssf_cost_volume launch per cloud (algorithmic, after the per-point split of the first layers)."""
+    per_row = 2 * m * m + 2 * (m * m + 3 * m + m * m) + 2 * (m * m + m * (m // 2) + m // 2)  # L2 x2, mlp3 x2, weightnet x2
+    per_point = 16 * per_row + 16 * 16 * m + 2 * 16 * 16 * m + 16 * m  # + QK^T, two mixes, forward cost
+    return 2.0 * n1 * per_point
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ssf_slam_b200 import _native as nat
+    from ssf_slam_b200 import functional as F_
+    from ssf_slam_b200 import profile as prof
+    from ssf_slam_b200 import synth
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200.shard import gather_results, my_sequences
+    from ssf_slam_b200.weights import random_init_state_dict
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.require_device()
+    B, N, K, Wm = args.batch, args.npoints, args.steps, args.warmup
+
+    # synthetic data: each rank owns its own sequences (config 4 sharding: seq_id % world == rank)
+    seqs = my_sequences(64, rank, world)
+    pool = synth.make_sequence(1000 + seqs[0], POOL, N)
+    p1 = np.stack([it["pos1"] for it in pool])
+    p2 = np.stack([it["pos2"] for it in pool])
+
+    def batch_ids(step):
+        return [(step * B + i) % POOL for i in range(B)]
+
+    sd = random_init_state_dict(0)
+    net = TFlow()
+    net.load_state_dict(sd, strict=True)
+    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10)
+    d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
+    dev_batches = [(d1[batch_ids(s)].contiguous(), d2[batch_ids(s)].contiguous()) for s in range(max(1, min(K + Wm, POOL)))]
+
+    def device_step(s, keep):
+        x1, x2 = dev_batches[s % len(dev_batches)]
+        flows, _ = net.forward_pm(x1, x2)
+        mask, odom = F_.frontend(x1, flows[0], mode=1, tau=0.10)
+        keep.append((mask, odom))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    keep = []
+    for s in range(Wm):
+        device_step(s, keep)
+    keep.clear()
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = nat.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for s in range(K):
+        device_step(Wm + s, keep)
+    if world > 1:  # final gather of poses and masks (the only communication of the job)
+        gather_results(torch.stack([o for _, o in keep]), torch.stack([m for m, _ in keep]))
+    ev1.record()
+    sync_all()
+    launches = nat.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clk = clocks.stop()
+    keep.clear()
+
+    # ---- end to end from pinned host buffers
+    host_batches = [(torch.from_numpy(p1[batch_ids(s)]).pin_memory(), torch.from_numpy(p2[batch_ids(s)]).pin_memory())
+                    for s in range(max(1, min(K + Wm, POOL)))]
+    for s in range(Wm):
+        fe.process(*host_batches[s % len(host_batches)])
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(K):
+        out = fe.process(*host_batches[(Wm + s) % len(host_batches)])
+    e1.record()
+    sync_all()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    ems = float(ems.item())
+
+    # ---- per-kernel shares (CUDA events around every launch of ours, same workload, after the timed region)
+    prof.enable()
+    for s in range(min(K, 3)):
+        device_step(Wm + s, keep)
+    torch.cuda.synchronize()
+    shares = prof.summary()
+    prof.disable()
+    keep.clear()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    top = max(shares.items(), key=lambda kv: kv[1]["ms"])[0] if shares else None
+    roof = None
+    if top is not None:
+        t = shares[top]
+        # the cost-volume core dominates; its level-0 launch (N1 = N, m = 64) is the single largest kernel
+        if top.startswith("cost_volume"):
+            flops = B * sum(cost_volume_flops(n1, m) for n1, m in ((N, 64), (2048, 64), (512, 128), (256, 256))) / 4.0
+            ach = flops / (t["ms"] / t["calls"] * 1e-3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["source"],
+                    "note": "fp32 FFMA realisation (fp32 parity path); algorithmic 2*MAC averaged over the 4 pyramid levels' launches"}
+        else:
+            roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
+                    "traffic": None, "peak_source": pk["source"]}
+
+    value = world * B * K / (ms * 1e-3)
+    e2e = world * B * K / (ems * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic CARLA-shaped clouds (ssf_slam_b200/synth.py), random-init TFlow weights (seed 0)",
+            "config": {"workload": "configs[1]: 200-frame synthetic sequence shaped like rm_road/SF/00, N=%d, "
+                                   "noSeg_ActiveSceneFlow pipeline (flow + dynamic mask + ego-motion)" % N,
+                       "pairs_per_step_per_gpu": B, "distinct_pairs": POOL, "sharding": "sequence id %% world (config 4), no "
+                       "collective on the hot path; one final all_gather of poses+masks",
+                       "l2": "per-step working set (~%.1f GB of intermediates) exceeds the 126 MB L2" % (B * 0.12)},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes(B, N), "d2h_bytes_per_step": fe.d2h_bytes(B, N),
+                    "ms_per_step": ems / K},
+            "roofline": roof, "kernel_shares": {k: round(v["share"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+
+    if not args.no_cpu_baseline and world == 1:
+        import torch as _t
+        t = cpu_pipeline_seconds(pool, 1, sd)  # warm-up
+        t = cpu_pipeline_seconds(pool, args.cpu_sample, sd)
+        line["cpu_baseline"] = {"value": len(t) / float(sum(t)), "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                                "sample": "%d frame pairs (N=%d): oracle TFlow port + sklearn GMM mask + slove_RT_by_SVD" % (len(t), N)}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

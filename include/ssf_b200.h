@@ -1,0 +1,130 @@
+/*
+ * ssf_b200.h -- C ABI of the B200-native SSF-SLAM scene-flow front end (libssf_b200.so).
+ *
+ * Every entry point takes plain DEVICE pointers, sizes and a CUDA stream (`void* stream` is a cudaStream_t);
+ * nothing allocates, nothing synchronises, outputs are caller-owned.  Return value: 0 = ok, 1 = bad
+ * argument, 2 = CUDA error; `ssf_last_error()` holds the message.  There is no CPU fallback.
+ *
+ * Each declaration cites the reference interface it replaces.  `ASF/` = scripts/ActiveSceneFlow/ in
+ * YQChen8/SSF-SLAM.  The reference reaches these through the Python module `lib.pointnet2_utils`
+ * (absent from its tree: .gitignore:74, README.md:22-27) and `torch_scatter`; INTEGRATION.md shows the
+ * ctypes binding that re-creates that module on top of this header.
+ *
+ * Layouts: "cm" = the reference's channel-major [B,C,N]; "pm" = point-major [B,N,C] (internal, fused path).
+ * dtypes: float = fp32, int = int32.
+ */
+#ifndef SSF_B200_H
+#define SSF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plumbing ---- */
+int ssf_abi_version(void);
+const char* ssf_last_error(void);
+unsigned long long ssf_launch_count(void);   /* kernels launched by this library so far */
+int ssf_require_device(void);                 /* non-zero unless the current device is sm_100 */
+
+/* ---- B-op: lib.pointnet2_utils drop-ins (reference layouts) ---- */
+
+/* furthest_point_sample(xyz[B,N,3], npoint) -> idx[B,npoint]; call site ASF/utils/utils.py:226.
+ * First index 0, running min initialised 1e10, argmax ties -> lowest index. N <= 131072. */
+int ssf_furthest_point_sample(const float* xyz, int B, int N, int npoint, int* idx, void* stream);
+
+/* gather_operation(features cm[B,C,N], idx[B,M]) -> cm[B,C,M]; ASF/utils/utils.py:228 */
+int ssf_gather_operation(const float* feat, const int* idx, int B, int C, int N, int M, float* out, void* stream);
+
+/* knn(k, unknown[B,Nq,3], known[B,Nr,3]) -> (dist[B,Nq,k] = sqrt(L2^2) ascending, idx[B,Nq,k]);
+ * ASF/utils/utils.py:229,291; ASF/utils/soflow.py:387-391,406,1243,1461.  Order: (distance, index)
+ * lexicographic; distances are ((dx*dx)+(dy*dy))+(dz*dz) without FMA.  dist may be NULL.  1 <= k <= 32, k <= Nr. */
+int ssf_knn(int k, const float* query, const float* ref, int B, int Nq, int Nr, float* dist, int* idx, void* stream);
+
+/* same, with the query formed on the fly as query + query_add (one rounded fp32 add per coordinate), i.e.
+ * `pointutils.knn(nsample, xyz1 + sf, xyz2)` at ASF/utils/soflow.py:389 without materialising the sum */
+int ssf_knn_offset(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,
+                   float* dist, int* idx, void* stream);
+
+/* three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3], idx[B,n,3]); ASF/utils/soflow.py:1241,1459 */
+int ssf_three_nn(const float* query, const float* ref, int B, int Nq, int Nr, float* dist, int* idx, void* stream);
+
+/* ball_query(radius, nsample, xyz[B,N,3], new_xyz[B,S,3]) -> idx[B,S,nsample] (+ cnt[B,S] hits in range, may be
+ * NULL); semantics of ASF/SetCover.py:39-63 (d <= r*r, ascending index, pad with first hit; no hit -> zeros) */
+int ssf_ball_query(float radius, int nsample, const float* xyz, const float* new_xyz, int B, int N, int S, int* idx,
+                   int* cnt, void* stream);
+
+/* grouping_operation(features cm[B,C,N], idx[B,M,S]) -> cm[B,C,M,S]; ASF/utils/utils.py:231,233,296,302;
+ * ASF/utils/soflow.py:30,1244,1249,1462,1470 */
+int ssf_grouping_operation(const float* feat, const int* idx, int B, int C, int N, int M, int S, float* out,
+                           void* stream);
+
+/* three_interpolate(features cm[B,C,M], idx[B,N,3], weight[B,N,3]) -> cm[B,C,N] (upstream pointnet2 API; the
+ * reference spells it as grouping * weight -> sum at ASF/utils/soflow.py:1462-1471) */
+int ssf_three_interpolate(const float* feat, const int* idx, const float* weight, int B, int C, int M, int N,
+                          float* out, void* stream);
+
+/* ---- B-scatter: torch_scatter drop-ins (ASF/utils/soflow.py:474,481), deterministic ---- */
+
+/* CSR of the key lists: workspace = ssf_csr_workspace_ints(B,L,n_seg) int32s; keys outside [0,n_seg) are skipped */
+long long ssf_csr_workspace_ints(int B, int L, int n_seg);
+int ssf_build_csr_i64(const long long* key, int B, int L, int n_seg, int* ws, void* stream);
+int ssf_build_csr_i32(const int* key, int B, int L, int n_seg, int* ws, void* stream);
+/* scatter_softmax(src[B,L,C], index, dim=1) -> [B,L,C] */
+int ssf_segment_softmax(const float* src, const int* csr_ws, int B, int L, int C, int n_seg, float* out, void* stream);
+/* scatter_sum(src[B,L,C], index, dim=1) -> [B,n_seg,C]; rows added in ascending l */
+int ssf_segment_sum(const float* src, const int* csr_ws, int B, int L, int C, int n_seg, float* out, void* stream);
+/* fused: out[b,j,:] = sum_l softmax_seg(logit)[l] * val[l,:]  (the backward cost, soflow.py:471-481) */
+int ssf_segment_softmax_sum(const float* logit, const float* val, const int* csr_ws, int B, int L, int C, int n_seg,
+                            float* out, void* stream);
+
+/* ---- B-layer: fused building blocks of TFlow (point-major, K-major BN-folded weights) ---- */
+
+/* y = clamp2(clamp1(act(x1.Wt[off1:] + x2.Wt[off2:] + bias)) + add); act 0 none / 1 ReLU / 2 LeakyReLU(0.1).
+ * All 1x1 Conv1d layers: ASF/TFlowV3_Occlussion.py:22-38,68,98-100; ASF/utils/utils.py:312-313;
+ * ASF/utils/soflow.py:511-525 (flow_mlp, fc, clamp +-50, + sf, clamp) and the per-point halves of split convs */
+int ssf_linear(const float* x1, int c1, int ld1, const float* x2, int c2, int ld2, const float* Wt, int ldw,
+               int w_off1, int w_off2, const float* bias, int rows, int cout, int act, float clamp1, const float* add,
+               int ld_add, float clamp2, float* y, int ldy, void* stream);
+
+/* pm row gather: out[b,m,:] = src[b,idx[b,m],:]  (new_xyz = xyz[fps_idx], ASF/utils/utils.py:228) */
+int ssf_gather_rows(const float* src, const int* idx, int B, int N, int M, int C, float* out, void* stream);
+
+/* [B,R,C] -> [B,C,R] */
+int ssf_transpose(const float* in, int B, int R, int C, float* out, void* stream);
+
+/* UpsampleFlow.forward (mode 0, clamp 100; ASF/utils/soflow.py:1443-1475) and the interpolation + warp of
+ * PointWarping.forward (mode 1, clamp 10; ASF/utils/soflow.py:1244-1257), given the neighbour indices */
+int ssf_interpolate(const float* query, const float* src_pos, const float* src_val, const int* idx, int B, int N,
+                    int M, int C, int k, int mode, float clampv, float* out, void* stream);
+
+/* gather -> MLP -> max over S: PointNetSetAbstraction.forward (ASF/utils/utils.py:231-247), the mlp1 half of
+ * PointNetSetUpConv.forward (:296-307) and mlp_convs4 + max of PointConvTransFlowV2 (ASF/utils/soflow.py:489-509).
+ * G/H are the first layer's per-point partial products; S in {8,16}; widths multiples of 32, hidden <= 256. */
+int ssf_group_mlp_max(const float* G, const float* H, const float* bias1, const float* Wd, const float* pos_src,
+                      const float* pos_q, const int* idx, const float* W2t, const float* b2, int C2, const float* W3t,
+                      const float* b3, int C3, int B, int Nsrc, int Nq, int S, int C1, int act, float* out, void* stream);
+
+/* PointConvTransFlowV2.forward core (ASF/utils/soflow.py:397-469,486): both branches, SxS attention, mlp_convs3,
+ * weightnet1, forward cost; emits warped-branch logits gw[B,N1*16] and rows Cw[B,N1*16,m]; m in {64,128,256} */
+int ssf_cost_volume(const float* Gab, const float* Hab, const float* W2a, const float* b2a, const float* W2w,
+                    const float* b2w, const float* W3a, const float* H3, const float* W3d, const float* W3b,
+                    const float* b3b, const float* Wn1, const float* bn1, const float* Wn2, const float* bn2,
+                    const float* wn3, float bn3, const float* xyz1, const float* xyz2, const int* idx, const int* idxw,
+                    int B, int N1, int N2, int m, float* cost_fwd, float* cost_fwd_cm, float* gw, float* Cw, void* stream);
+
+/* ---- B-frontend: dynamic mask + static-point ego-motion (ASF/main_sju_occ_ros.py:257-284,455-473;
+ * scripts/PointCloudOdometry.py:15-33,91-101) ----
+ * mode 0: weighted Kabsch on the points whose in_mask is 0 (GT / dataset mask variants);
+ * mode 2: as mode 0 with `flow` holding the source cloud itself: slove_RT_by_SVD(src = flow, dst = points);
+ * mode 1: residual-vs-rigid-flow masker with optional semantic seed (movable class bitmask) and per-instance
+ *         voting, then Kabsch on the static set.  Bit-level spec: oracle/frontend.py::masker_spec.
+ * points, flow [B,N,3]; mask_out u8 [B,N] (1 = dynamic); odom_out f64 [B,7] = [tx,ty,tz,qx,qy,qz,qw]
+ * (the frame_odom1 payload); pose_out f64 [B,12] = [R row-major | t] or NULL. */
+int ssf_frontend(const float* points, const float* flow, int B, int N, int mode, const unsigned char* in_mask,
+                 const int* sem, unsigned long long movable_bits, const int* inst, int n_inst, float tau,
+                 unsigned char* mask_out, double* odom_out, double* pose_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSF_B200_H */

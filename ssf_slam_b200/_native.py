@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI declared in ``include/ssf_b200.h`` (``libssf_b200.so``).
+
+PyTorch is only plumbing here: it owns device memory and the stream; every kernel is ours and is called
+through the C ABI with raw device pointers.  There is no fallback: a missing library, a non-CUDA tensor or
+a non-sm_100 device raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssf_b200.so")
+
+_P, _I, _F, _U64, _I64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_longlong
+_CODES = {"p": _P, "i": _I, "f": _F, "Q": _U64, "q": _I64}
+
+# name -> (argument codes, restype); mirrors include/ssf_b200.h one to one
+SIGNATURES = {
+    "ssf_abi_version": ("", _I),
+    "ssf_last_error": ("", ctypes.c_char_p),
+    "ssf_launch_count": ("", _U64),
+    "ssf_require_device": ("", _I),
+    "ssf_furthest_point_sample": ("piiipp", _I),
+    "ssf_gather_operation": ("ppiiiipp", _I),
+    "ssf_knn": ("ippiiippp", _I),
+    "ssf_knn_offset": ("ipppiiippp", _I),
+    "ssf_three_nn": ("ppiiippp", _I),
+    "ssf_ball_query": ("fippiiippp", _I),
+    "ssf_grouping_operation": ("ppiiiiipp", _I),
+    "ssf_three_interpolate": ("pppiiiipp", _I),
+    "ssf_csr_workspace_ints": ("iii", _I64),
+    "ssf_build_csr_i64": ("piiipp", _I),
+    "ssf_build_csr_i32": ("piiipp", _I),
+    "ssf_segment_softmax": ("ppiiiipp", _I),
+    "ssf_segment_sum": ("ppiiiipp", _I),
+    "ssf_segment_softmax_sum": ("pppiiiipp", _I),
+    "ssf_linear": ("piipiipiiipiiifpifpip", _I),
+    "ssf_gather_rows": ("ppiiiipp", _I),
+    "ssf_transpose": ("piiipp", _I),
+    "ssf_interpolate": ("ppppiiiiiifpp", _I),
+    "ssf_group_mlp_max": ("ppppppp" + "ppi" + "ppi" + "iiiiii" + "pp", _I),
+    "ssf_cost_volume": ("p" * 16 + "f" + "pppp" + "iiii" + "pppp" + "p", _I),
+    "ssf_frontend": ("ppiiippQpifpppp", _I),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libssf_b200.so (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -m ssf_slam_b200.build` (or __graft_entry__.build()); "
+                               "ssf_slam_b200 has no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (codes, res) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = [_CODES[c] for c in codes]
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+class SsfError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise SsfError(lib().ssf_last_error().decode())
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SsfError("ssf_slam_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+    if not t.is_contiguous():
+        raise SsfError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().ssf_launch_count())
+
+
+_device_ok = False
+
+
+def require_device():
+    global _device_ok
+    if not _device_ok:
+        if not torch.cuda.is_available():
+            raise SsfError("no CUDA device: ssf_slam_b200 runs on B200 (sm_100a) only")
+        check(lib().ssf_require_device())
+        _device_ok = True

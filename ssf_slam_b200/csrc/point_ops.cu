@@ -1,0 +1,747 @@
+// Point operators of the SSF-SLAM scene-flow front end, hand-written for sm_100a.
+//
+// Drop-in replacements for the reference's absent pointnet2 extension (`lib.pointnet2_utils`,
+// call sites ASF/utils/utils.py:226-233,291-302 and ASF/utils/soflow.py:30,387-406,1241-1249,
+// 1459-1470) and for torch_scatter (ASF/utils/soflow.py:474,481).  Arithmetic and tie-breaking follow
+// the written spec: no-FMA squared distances, (distance, index) lexicographic
+// kNN order, FPS from index 0 with lowest-index argmax.
+//
+//  * furthest_point_sample : one CTA per cloud, points and running minima in registers, argmax by two
+//    redux.sync per warp + one shared-memory hop; clouds larger than one CTA's registers run on a
+//    thread-block cluster and exchange candidates through distributed shared memory.
+//  * knn / three_nn / ball_query : thread per query, reference cloud streamed through shared memory in
+//    double-buffered tiles by the TMA engine (cp.async.bulk + mbarrier), float4 shared loads.
+//  * grouping / gather / three_interpolate : vectorised gathers with streaming stores.
+//  * scatter softmax / sum : deterministic (atomic-free accumulation) through a CSR of the key lists.
+#include <cooperative_groups.h>
+
+#include "ssf_common.cuh"
+
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------ FPS
+
+// One CTA per cloud.  Thread t owns points t, t+T, ...; xyz also sits in shared memory so that the
+// coordinates of the winner can be broadcast without a global round trip.
+template <int T, int PPT>
+__global__ void __launch_bounds__(T, 1)
+fps_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ out) {
+    extern __shared__ float s_xyz[];
+    __shared__ unsigned s_val[2][32];
+    __shared__ unsigned s_idx[2][32];
+    constexpr int NW = T / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* p = xyz + (size_t)blockIdx.x * N * 3;
+    int* o = out + (size_t)blockIdx.x * npoint;
+    for (int i = tid; i < N * 3; i += T) s_xyz[i] = p[i];
+    __syncthreads();
+
+    float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        int i = tid + j * T;
+        bool ok = i < N;
+        px[j] = ok ? s_xyz[3 * i] : 0.f;
+        py[j] = ok ? s_xyz[3 * i + 1] : 0.f;
+        pz[j] = ok ? s_xyz[3 * i + 2] : 0.f;
+        md[j] = 1e10f;
+    }
+    int last = 0;
+    for (int it = 0; it < npoint; ++it) {
+        if (tid == 0) o[it] = last;
+        if (it == npoint - 1) break;
+        const float lx = s_xyz[3 * last], ly = s_xyz[3 * last + 1], lz = s_xyz[3 * last + 2];
+        float best = -1.f;
+        unsigned besti = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            int i = tid + j * T;
+            if (i < N) {
+                float d = ssf_sqdist(px[j], py[j], pz[j], lx, ly, lz);
+                float m = fminf(md[j], d);
+                md[j] = m;
+                if (m > best) {
+                    best = m;
+                    besti = (unsigned)i;
+                }
+            }
+        }
+        // non-negative floats order like their bit patterns; ties resolve to the lowest index
+        unsigned vb = besti == 0xffffffffu ? 0u : __float_as_uint(best);
+        unsigned wm = __reduce_max_sync(0xffffffffu, vb);
+        unsigned wi = __reduce_min_sync(0xffffffffu, vb == wm ? besti : 0xffffffffu);
+        const int buf = it & 1;
+        if (lane == 0) {
+            s_val[buf][warp] = wm;
+            s_idx[buf][warp] = wi;
+        }
+        __syncthreads();
+        unsigned v2 = lane < NW ? s_val[buf][lane] : 0u;
+        unsigned i2 = lane < NW ? s_idx[buf][lane] : 0xffffffffu;
+        unsigned gm = __reduce_max_sync(0xffffffffu, v2);
+        last = (int)__reduce_min_sync(0xffffffffu, v2 == gm ? i2 : 0xffffffffu);
+    }
+}
+
+// Cluster variant: CS CTAs of 1024 threads share one cloud (N <= CS * 1024 * PPT); each CTA keeps its slice
+// in registers and publishes its candidate (value, index, xyz) into every peer's shared memory (DSMEM),
+// one cluster barrier per iteration.
+struct FpsCand {
+    unsigned val;
+    unsigned idx;
+    float x, y, z;
+    float pad[3];
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(1024, 1)
+fps_cluster_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ out) {
+    constexpr int T = 1024;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / cs;
+    __shared__ unsigned s_val[32];
+    __shared__ unsigned s_idx[32];
+    __shared__ FpsCand s_cand[2][16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* p = xyz + (size_t)cloud * N * 3;
+    int* o = out + (size_t)cloud * npoint;
+    const int slice = (N + cs - 1) / cs;
+    const int lo = rank * slice;
+    const int hi = min(N, lo + slice);
+
+    float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        int i = lo + tid + j * T;
+        bool ok = i < hi;
+        px[j] = ok ? p[3 * i] : 0.f;
+        py[j] = ok ? p[3 * i + 1] : 0.f;
+        pz[j] = ok ? p[3 * i + 2] : 0.f;
+        md[j] = 1e10f;
+    }
+    int last = 0;
+    float lx = p[0], ly = p[1], lz = p[2];
+    cluster.sync();
+    for (int it = 0; it < npoint; ++it) {
+        if (rank == 0 && tid == 0) o[it] = last;
+        if (it == npoint - 1) break;
+        float best = -1.f;
+        unsigned besti = 0xffffffffu;
+        int bestj = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            int i = lo + tid + j * T;
+            if (i < hi) {
+                float d = ssf_sqdist(px[j], py[j], pz[j], lx, ly, lz);
+                float m = fminf(md[j], d);
+                md[j] = m;
+                if (m > best) {
+                    best = m;
+                    besti = (unsigned)i;
+                    bestj = j;
+                }
+            }
+        }
+        unsigned vb = besti == 0xffffffffu ? 0u : __float_as_uint(best);
+        unsigned wm = __reduce_max_sync(0xffffffffu, vb);
+        unsigned wi = __reduce_min_sync(0xffffffffu, vb == wm ? besti : 0xffffffffu);
+        if (lane == 0) {
+            s_val[warp] = wm;
+            s_idx[warp] = wi;
+        }
+        __syncthreads();
+        unsigned v2 = s_val[lane];
+        unsigned i2 = s_idx[lane];
+        unsigned gm = __reduce_max_sync(0xffffffffu, v2);
+        unsigned gi = __reduce_min_sync(0xffffffffu, v2 == gm ? i2 : 0xffffffffu);
+        const int buf = it & 1;
+        // the owner of the CTA-level winner publishes it to every CTA of the cluster
+        if (gi != 0xffffffffu && besti == gi) {
+            float wx = 0.f, wy = 0.f, wz = 0.f;
+#pragma unroll
+            for (int j = 0; j < PPT; ++j)
+                if (j == bestj) {
+                    wx = px[j];
+                    wy = py[j];
+                    wz = pz[j];
+                }
+            for (int r = 0; r < cs; ++r) {
+                FpsCand* dst = cluster.map_shared_rank(&s_cand[buf][rank], r);
+                dst->val = gm;
+                dst->idx = gi;
+                dst->x = wx;
+                dst->y = wy;
+                dst->z = wz;
+            }
+        } else if (gi == 0xffffffffu && tid == 0) {  // empty slice
+            for (int r = 0; r < cs; ++r) {
+                FpsCand* dst = cluster.map_shared_rank(&s_cand[buf][rank], r);
+                dst->val = 0u;
+                dst->idx = 0xffffffffu;
+            }
+        }
+        cluster.sync();
+        unsigned cv = lane < cs ? s_cand[buf][lane].val : 0u;
+        unsigned ci = lane < cs ? s_cand[buf][lane].idx : 0xffffffffu;
+        unsigned cm = __reduce_max_sync(0xffffffffu, cv);
+        unsigned win = __reduce_min_sync(0xffffffffu, cv == cm ? ci : 0xffffffffu);
+        int src = __ffs(__ballot_sync(0xffffffffu, lane < cs && cv == cm && ci == win)) - 1;
+        last = (int)win;
+        lx = s_cand[buf][src].x;
+        ly = s_cand[buf][src].y;
+        lz = s_cand[buf][src].z;
+    }
+    cluster.sync();  // no CTA may exit while peers can still write into its shared memory
+}
+
+template <int T, int PPT>
+static int launch_fps(const float* xyz, int B, int N, int npoint, int* out, cudaStream_t st) {
+    size_t smem = (size_t)N * 3 * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fps_kernel<T, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return ssf_set_error(e);
+    }
+    fps_kernel<T, PPT><<<B, T, smem, st>>>(xyz, N, npoint, out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+template <int PPT>
+static int launch_fps_cluster(const float* xyz, int B, int N, int npoint, int* out, int cs, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * cs);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cs > 8) {
+        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return ssf_set_error(e);
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT>, xyz, N, npoint, out);
+    ssf_count_launch();
+    if (e != cudaSuccess) return ssf_set_error(e);
+    return SSF_OK;
+}
+
+extern "C" int ssf_furthest_point_sample(const float* xyz, int B, int N, int npoint, int* idx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || npoint <= 0) return ssf_arg_error("furthest_point_sample: empty input");
+    if (N <= 128) return launch_fps<128, 1>(xyz, B, N, npoint, idx, st);
+    if (N <= 256) return launch_fps<128, 2>(xyz, B, N, npoint, idx, st);
+    if (N <= 512) return launch_fps<256, 2>(xyz, B, N, npoint, idx, st);
+    if (N <= 1024) return launch_fps<256, 4>(xyz, B, N, npoint, idx, st);
+    if (N <= 2048) return launch_fps<512, 4>(xyz, B, N, npoint, idx, st);
+    if (N <= 4096) return launch_fps<1024, 4>(xyz, B, N, npoint, idx, st);
+    if (N <= 8192) return launch_fps<1024, 8>(xyz, B, N, npoint, idx, st);
+    if (N <= 16384) return launch_fps_cluster<8>(xyz, B, N, npoint, idx, 2, st);
+    if (N <= 32768) return launch_fps_cluster<8>(xyz, B, N, npoint, idx, 4, st);
+    if (N <= 65536) return launch_fps_cluster<8>(xyz, B, N, npoint, idx, 8, st);
+    if (N <= 131072) return launch_fps_cluster<8>(xyz, B, N, npoint, idx, 16, st);
+    return ssf_arg_error("furthest_point_sample: N > 131072 not supported");
+}
+
+// ------------------------------------------------------------------------- tiled reference scan
+
+constexpr int SCAN_T = 128;      // threads (= queries) per CTA
+constexpr int SCAN_TILE = 1024;  // reference points per shared-memory tile (12 KB), double buffered
+
+// Streams ref[b] through shared memory and calls op(x, y, z, global_index) for every reference point, in
+// ascending index order.  The bulk-copy (TMA) path needs 16-byte aligned sources and sizes; ragged tiles
+// fall back to cooperative loads.
+template <class Op>
+__device__ __forceinline__ void scan_reference(const float* __restrict__ refb, int Nr, float* tiles, uint64_t* bars, Op& op) {
+    const int tid = threadIdx.x;
+    const int ntiles = (Nr + SCAN_TILE - 1) / SCAN_TILE;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(refb) & 15) == 0;
+    auto issue = [&](int t) {
+        const int cnt = min(SCAN_TILE, Nr - t * SCAN_TILE);
+        float* dst = tiles + (t & 1) * SCAN_TILE * 3;
+        const float* src = refb + (size_t)t * SCAN_TILE * 3;
+        const bool bulk = base_aligned && ((cnt * 12) % 16 == 0);
+        if (bulk) {
+            if (tid == 0) {
+                ssf_mbar_expect_tx(&bars[t & 1], (uint32_t)cnt * 12u);
+                ssf_bulk_g2s(dst, src, (uint32_t)cnt * 12u, &bars[t & 1]);
+            }
+        } else {
+            for (int i = tid; i < cnt * 3; i += SCAN_T) dst[i] = src[i];
+        }
+        return bulk;
+    };
+    // `bulk` is a block-uniform function of (t): recompute instead of storing
+    auto is_bulk = [&](int t) {
+        const int cnt = min(SCAN_TILE, Nr - t * SCAN_TILE);
+        return base_aligned && ((cnt * 12) % 16 == 0);
+    };
+    unsigned phases = 0u;  // bit i = parity to wait for on bars[i]
+    issue(0);
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) issue(t + 1);
+        const int cur = t & 1;
+        if (is_bulk(t)) {
+            ssf_mbar_wait(&bars[cur], (phases >> cur) & 1u);
+            phases ^= 1u << cur;
+        } else {
+            __syncthreads();
+        }
+        const float* tp = tiles + cur * SCAN_TILE * 3;
+        const int cnt = min(SCAN_TILE, Nr - t * SCAN_TILE);
+        const int base = t * SCAN_TILE;
+        const float4* t4 = reinterpret_cast<const float4*>(tp);
+        const int n4 = cnt >> 2;
+        for (int g = 0; g < n4; ++g) {
+            const float4 a = t4[3 * g], b = t4[3 * g + 1], c = t4[3 * g + 2];
+            const int r = base + 4 * g;
+            op(a.x, a.y, a.z, r);
+            op(a.w, b.x, b.y, r + 1);
+            op(b.z, b.w, c.x, r + 2);
+            op(c.y, c.z, c.w, r + 3);
+        }
+        for (int r = n4 << 2; r < cnt; ++r) op(tp[3 * r], tp[3 * r + 1], tp[3 * r + 2], base + r);
+        __syncthreads();  // everyone is done with this buffer before it is refilled
+    }
+}
+
+template <int K>
+struct KnnOp {
+    float qx, qy, qz;
+    float bd[K];
+    int bi[K];
+    __device__ __forceinline__ void operator()(float x, float y, float z, int r) {
+        const float d = ssf_sqdist(qx, qy, qz, x, y, z);
+        // candidates arrive in ascending index: strict '<' keeps the lowest index on equal distance
+        if (d < bd[K - 1]) {
+            bd[K - 1] = d;
+            bi[K - 1] = r;
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                if (bd[j] < bd[j - 1]) {
+                    float td = bd[j];
+                    bd[j] = bd[j - 1];
+                    bd[j - 1] = td;
+                    int ti = bi[j];
+                    bi[j] = bi[j - 1];
+                    bi[j - 1] = ti;
+                }
+            }
+        }
+    }
+};
+
+// query [B,Nq,3] (+ optional per-query offset qadd [B,Nq,3], added with one rounded fp32 add exactly as
+// `xyz1 + sf` at ASF/utils/soflow.py:389), ref [B,Nr,3] -> dist [B,Nq,k] (may be null), idx [B,Nq,k]
+template <int K>
+__global__ void __launch_bounds__(SCAN_T)
+knn_kernel(const float* __restrict__ query, const float* __restrict__ qadd, const float* __restrict__ ref, int Nq, int Nr,
+           int k, float* __restrict__ dist, int* __restrict__ idx) {
+    __shared__ __align__(128) float tiles[2 * SCAN_TILE * 3];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * SCAN_T + threadIdx.x;
+    if (threadIdx.x == 0) {
+        ssf_mbar_init(&bars[0], 1);
+        ssf_mbar_init(&bars[1], 1);
+        ssf_mbar_fence_init();
+    }
+    __syncthreads();
+    KnnOp<K> op;
+    const int qq = min(q, Nq - 1);
+    const float* qp = query + ((size_t)b * Nq + qq) * 3;
+    op.qx = qp[0];
+    op.qy = qp[1];
+    op.qz = qp[2];
+    if (qadd != nullptr) {
+        const float* ap = qadd + ((size_t)b * Nq + qq) * 3;
+        op.qx = __fadd_rn(op.qx, ap[0]);
+        op.qy = __fadd_rn(op.qy, ap[1]);
+        op.qz = __fadd_rn(op.qz, ap[2]);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        op.bd[j] = __int_as_float(0x7f800000);
+        op.bi[j] = 0;
+    }
+    scan_reference(ref + (size_t)b * Nr * 3, Nr, tiles, bars, op);
+    if (q < Nq) {
+        const size_t o = ((size_t)b * Nq + q) * k;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < k) {
+                idx[o + j] = op.bi[j];
+                if (dist != nullptr) dist[o + j] = __fsqrt_rn(op.bd[j]);
+            }
+        }
+    }
+}
+
+extern "C" int ssf_knn_offset(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,
+                              float* dist, int* idx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || Nq <= 0) return ssf_arg_error("knn: empty input");
+    if (k <= 0 || k > 32) return ssf_arg_error("knn: k must be in [1,32]");
+    if (k > Nr) return ssf_arg_error("knn: k exceeds the number of reference points");
+    dim3 grid((Nq + SCAN_T - 1) / SCAN_T, B);
+    if (k <= 3)
+        knn_kernel<3><<<grid, SCAN_T, 0, st>>>(query, query_add, ref, Nq, Nr, k, dist, idx);
+    else if (k <= 5)
+        knn_kernel<5><<<grid, SCAN_T, 0, st>>>(query, query_add, ref, Nq, Nr, k, dist, idx);
+    else if (k <= 8)
+        knn_kernel<8><<<grid, SCAN_T, 0, st>>>(query, query_add, ref, Nq, Nr, k, dist, idx);
+    else if (k <= 16)
+        knn_kernel<16><<<grid, SCAN_T, 0, st>>>(query, query_add, ref, Nq, Nr, k, dist, idx);
+    else
+        knn_kernel<32><<<grid, SCAN_T, 0, st>>>(query, query_add, ref, Nq, Nr, k, dist, idx);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+extern "C" int ssf_knn(int k, const float* query, const float* ref, int B, int Nq, int Nr, float* dist, int* idx,
+                       void* stream) {
+    return ssf_knn_offset(k, query, nullptr, ref, B, Nq, Nr, dist, idx, stream);
+}
+
+extern "C" int ssf_three_nn(const float* query, const float* ref, int B, int Nq, int Nr, float* dist, int* idx,
+                            void* stream) {
+    return ssf_knn_offset(3, query, nullptr, ref, B, Nq, Nr, dist, idx, stream);
+}
+
+struct BallOp {
+    float qx, qy, qz, r2;
+    int nsample, cnt, first;
+    int* out;
+    __device__ __forceinline__ void operator()(float x, float y, float z, int r) {
+        const float d = ssf_sqdist(qx, qy, qz, x, y, z);
+        if (d <= r2) {
+            if (cnt == 0) first = r;
+            if (cnt < nsample && out != nullptr) out[cnt] = r;
+            ++cnt;
+        }
+    }
+};
+
+// xyz [B,N,3], new_xyz [B,S,3] -> idx [B,S,nsample], cnt [B,S] (may be null)
+__global__ void __launch_bounds__(SCAN_T)
+ball_query_kernel(float r2, int nsample, const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S,
+                  int* __restrict__ idx, int* __restrict__ cnt) {
+    __shared__ __align__(128) float tiles[2 * SCAN_TILE * 3];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * SCAN_T + threadIdx.x;
+    if (threadIdx.x == 0) {
+        ssf_mbar_init(&bars[0], 1);
+        ssf_mbar_init(&bars[1], 1);
+        ssf_mbar_fence_init();
+    }
+    __syncthreads();
+    BallOp op;
+    const int ss = min(s, S - 1);
+    const float* c = new_xyz + ((size_t)b * S + ss) * 3;
+    op.qx = c[0];
+    op.qy = c[1];
+    op.qz = c[2];
+    op.r2 = r2;
+    op.nsample = nsample;
+    op.cnt = 0;
+    op.first = 0;
+    op.out = s < S ? idx + ((size_t)b * S + s) * nsample : nullptr;
+    scan_reference(xyz + (size_t)b * N * 3, N, tiles, bars, op);
+    if (s < S) {
+        for (int j = min(op.cnt, nsample); j < nsample; ++j) op.out[j] = op.first;
+        if (cnt != nullptr) cnt[(size_t)b * S + s] = op.cnt;
+    }
+}
+
+extern "C" int ssf_ball_query(float radius, int nsample, const float* xyz, const float* new_xyz, int B, int N, int S,
+                              int* idx, int* cnt, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || S <= 0 || N <= 0 || nsample <= 0) return ssf_arg_error("ball_query: empty input");
+    const float r2 = radius * radius;  // fp32 product, as the spec
+    dim3 grid((S + SCAN_T - 1) / SCAN_T, B);
+    ball_query_kernel<<<grid, SCAN_T, 0, st>>>(r2, nsample, xyz, new_xyz, N, S, idx, cnt);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+// --------------------------------------------------------------------------------- gathers
+
+constexpr int GROUP_CH = 8;  // channels handled per thread (independent gathers in flight)
+
+// feat [B,C,N], idx [B,MS] -> out [B,C,MS]; 4 consecutive outputs per thread, streaming stores
+__global__ void __launch_bounds__(256)
+group_vec4_kernel(const float* __restrict__ feat, const int* __restrict__ idx, int C, int N, int MS4, float* __restrict__ out) {
+    const int j4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j4 >= MS4) return;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GROUP_CH;
+    const int4 id = __ldg(reinterpret_cast<const int4*>(idx) + (size_t)b * MS4 + j4);
+    const float* f = feat + ((size_t)b * C + c0) * N;
+    float4* o = reinterpret_cast<float4*>(out) + ((size_t)b * C + c0) * MS4 + j4;
+    float4 v[GROUP_CH];
+#pragma unroll
+    for (int c = 0; c < GROUP_CH; ++c) {
+        if (c0 + c < C) {
+            const float* fc = f + (size_t)c * N;
+            v[c] = make_float4(__ldg(fc + id.x), __ldg(fc + id.y), __ldg(fc + id.z), __ldg(fc + id.w));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < GROUP_CH; ++c)
+        if (c0 + c < C) __stcs(o + (size_t)c * MS4, v[c]);
+}
+
+__global__ void __launch_bounds__(256)
+group_scalar_kernel(const float* __restrict__ feat, const int* __restrict__ idx, int C, int N, int MS, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= MS) return;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GROUP_CH;
+    const int id = __ldg(idx + (size_t)b * MS + j);
+    const float* f = feat + ((size_t)b * C + c0) * N;
+    float* o = out + ((size_t)b * C + c0) * MS + j;
+#pragma unroll
+    for (int c = 0; c < GROUP_CH; ++c)
+        if (c0 + c < C) o[(size_t)c * MS] = __ldg(f + (size_t)c * N + id);
+}
+
+extern "C" int ssf_grouping_operation(const float* feat, const int* idx, int B, int C, int N, int M, int S, float* out,
+                                      void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long MS = (long long)M * S;
+    if (B <= 0 || C <= 0 || MS <= 0) return ssf_arg_error("grouping_operation: empty input");
+    const bool vec = (MS % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+        const int MS4 = (int)(MS / 4);
+        dim3 grid((MS4 + 255) / 256, (C + GROUP_CH - 1) / GROUP_CH, B);
+        group_vec4_kernel<<<grid, 256, 0, st>>>(feat, idx, C, N, MS4, out);
+    } else {
+        dim3 grid((unsigned)((MS + 255) / 256), (C + GROUP_CH - 1) / GROUP_CH, B);
+        group_scalar_kernel<<<grid, 256, 0, st>>>(feat, idx, C, N, (int)MS, out);
+    }
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+extern "C" int ssf_gather_operation(const float* feat, const int* idx, int B, int C, int N, int M, float* out, void* stream) {
+    return ssf_grouping_operation(feat, idx, B, C, N, M, 1, out, stream);
+}
+
+// feat [B,C,M], idx [B,N,3], weight [B,N,3] -> out [B,C,N] = (g0*w0 + g1*w1) + g2*w2, every op rounded
+__global__ void __launch_bounds__(256)
+three_interpolate_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const float* __restrict__ w, int C,
+                         int M, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * GROUP_CH;
+    const int* ip = idx + ((size_t)b * N + n) * 3;
+    const float* wp = w + ((size_t)b * N + n) * 3;
+    const int i0 = ip[0], i1 = ip[1], i2 = ip[2];
+    const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+#pragma unroll
+    for (int c = 0; c < GROUP_CH; ++c) {
+        if (c0 + c < C) {
+            const float* f = feat + ((size_t)b * C + c0 + c) * M;
+            float v = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(f + i0), w0), __fmul_rn(__ldg(f + i1), w1)),
+                                __fmul_rn(__ldg(f + i2), w2));
+            out[((size_t)b * C + c0 + c) * N + n] = v;
+        }
+    }
+}
+
+extern "C" int ssf_three_interpolate(const float* feat, const int* idx, const float* weight, int B, int C, int M, int N,
+                                     float* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || C <= 0 || N <= 0) return ssf_arg_error("three_interpolate: empty input");
+    dim3 grid((N + 255) / 256, (C + GROUP_CH - 1) / GROUP_CH, B);
+    three_interpolate_kernel<<<grid, 256, 0, st>>>(feat, idx, weight, C, M, N, out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+// --------------------------------------------------------- deterministic segmented softmax / sum
+
+// CSR of "which rows l carry key j", rows of a segment in ascending l.  Integer-only, so the result is
+// reproducible although the fill uses atomics (each segment is sorted afterwards).
+template <typename IdxT>
+__global__ void csr_count_kernel(const IdxT* __restrict__ key, int L, int n_seg, int* __restrict__ count) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (l >= L) return;
+    const long long k = (long long)key[(size_t)b * L + l];
+    if (k >= 0 && k < n_seg) atomicAdd(&count[(size_t)b * (n_seg + 1) + k], 1);
+}
+
+// in-place exclusive scan of count[b][0..n_seg] (n_seg+1 entries; the last becomes the total)
+__global__ void __launch_bounds__(1024) csr_scan_kernel(int* __restrict__ count, int n_seg) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    int* c = count + (size_t)blockIdx.x * (n_seg + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_seg + 1; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n_seg + 1 ? c[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int incl = x + (warp > 0 ? s_warp[warp - 1] : 0) + carry;
+        if (i < n_seg + 1) c[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+        __syncthreads();
+    }
+}
+
+template <typename IdxT>
+__global__ void csr_fill_kernel(const IdxT* __restrict__ key, int L, int n_seg, const int* __restrict__ offset,
+                                int* __restrict__ cursor, int* __restrict__ rows) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (l >= L) return;
+    const long long k = (long long)key[(size_t)b * L + l];
+    if (k < 0 || k >= n_seg) return;
+    const int pos = atomicAdd(&cursor[(size_t)b * n_seg + k], 1);
+    rows[(size_t)b * L + offset[(size_t)b * (n_seg + 1) + k] + pos] = l;
+}
+
+__global__ void csr_sort_kernel(const int* __restrict__ offset, int n_seg, int L, int* __restrict__ rows) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= n_seg) return;
+    const int* off = offset + (size_t)b * (n_seg + 1);
+    int* r = rows + (size_t)b * L;
+    const int lo = off[j], hi = off[j + 1];
+    for (int a = lo + 1; a < hi; ++a) {
+        const int v = r[a];
+        int p = a - 1;
+        while (p >= lo && r[p] > v) {
+            r[p + 1] = r[p];
+            --p;
+        }
+        r[p + 1] = v;
+    }
+}
+
+// workspace ints per batch item: (n_seg + 1) offsets + n_seg cursors + L rows
+extern "C" long long ssf_csr_workspace_ints(int B, int L, int n_seg) {
+    return (long long)B * ((long long)(n_seg + 1) + n_seg + L);
+}
+
+template <typename IdxT>
+static int build_csr(const IdxT* key, int B, int L, int n_seg, int* ws, cudaStream_t st) {
+    int* offset = ws;
+    int* cursor = ws + (size_t)B * (n_seg + 1);
+    int* rows = cursor + (size_t)B * n_seg;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(int) * ((size_t)B * (n_seg + 1) + (size_t)B * n_seg), st);
+    if (e != cudaSuccess) return ssf_set_error(e);
+    dim3 gl((L + 255) / 256, B);
+    csr_count_kernel<IdxT><<<gl, 256, 0, st>>>(key, L, n_seg, offset);
+    csr_scan_kernel<<<B, 1024, 0, st>>>(offset, n_seg);
+    csr_fill_kernel<IdxT><<<gl, 256, 0, st>>>(key, L, n_seg, offset, cursor, rows);
+    dim3 gs((n_seg + 127) / 128, B);
+    csr_sort_kernel<<<gs, 128, 0, st>>>(offset, n_seg, L, rows);
+    for (int i = 0; i < 4; ++i) ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+extern "C" int ssf_build_csr_i64(const long long* key, int B, int L, int n_seg, int* ws, void* stream) {
+    return build_csr<long long>(key, B, L, n_seg, ws, (cudaStream_t)stream);
+}
+extern "C" int ssf_build_csr_i32(const int* key, int B, int L, int n_seg, int* ws, void* stream) {
+    return build_csr<int>(key, B, L, n_seg, ws, (cudaStream_t)stream);
+}
+
+// src [B,L,C] -> out [B,L,C]: softmax over the rows of each segment, per channel (torch_scatter semantics)
+__global__ void __launch_bounds__(128)
+seg_softmax_kernel(const float* __restrict__ src, const int* __restrict__ ws, int B, int L, int C, int n_seg,
+                   float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_seg * C) return;
+    const int j = (int)(t / C), c = (int)(t % C);
+    const int* off = ws + (size_t)b * (n_seg + 1);
+    const int* rows = ws + (size_t)B * (n_seg + 1) + (size_t)B * n_seg + (size_t)b * L;
+    const float* s = src + (size_t)b * L * C;
+    float* o = out + (size_t)b * L * C;
+    const int lo = off[j], hi = off[j + 1];
+    float m = -INFINITY;
+    for (int a = lo; a < hi; ++a) m = fmaxf(m, s[(size_t)rows[a] * C + c]);
+    float den = 0.f;
+    for (int a = lo; a < hi; ++a) den += expf(s[(size_t)rows[a] * C + c] - m);
+    for (int a = lo; a < hi; ++a) {
+        const size_t p = (size_t)rows[a] * C + c;
+        o[p] = expf(s[p] - m) / den;
+    }
+}
+
+// src [B,L,C] -> out [B,n_seg,C]: rows of a segment added in ascending row order
+__global__ void __launch_bounds__(128)
+seg_sum_kernel(const float* __restrict__ src, const int* __restrict__ ws, int B, int L, int C, int n_seg,
+               float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_seg * C) return;
+    const int j = (int)(t / C), c = (int)(t % C);
+    const int* off = ws + (size_t)b * (n_seg + 1);
+    const int* rows = ws + (size_t)B * (n_seg + 1) + (size_t)B * n_seg + (size_t)b * L;
+    const float* s = src + (size_t)b * L * C;
+    const int lo = off[j], hi = off[j + 1];
+    float acc = 0.f;
+    for (int a = lo; a < hi; ++a) acc += s[(size_t)rows[a] * C + c];
+    out[((size_t)b * n_seg + j) * C + c] = acc;
+}
+
+extern "C" int ssf_segment_softmax(const float* src, const int* csr_ws, int B, int L, int C, int n_seg, float* out,
+                                   void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || L <= 0 || C <= 0 || n_seg <= 0) return ssf_arg_error("segment_softmax: empty input");
+    dim3 grid((unsigned)(((long long)n_seg * C + 127) / 128), B);
+    seg_softmax_kernel<<<grid, 128, 0, st>>>(src, csr_ws, B, L, C, n_seg, out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+extern "C" int ssf_segment_sum(const float* src, const int* csr_ws, int B, int L, int C, int n_seg, float* out,
+                               void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || L <= 0 || C <= 0 || n_seg <= 0) return ssf_arg_error("segment_sum: empty input");
+    dim3 grid((unsigned)(((long long)n_seg * C + 127) / 128), B);
+    seg_sum_kernel<<<grid, 128, 0, st>>>(src, csr_ws, B, L, C, n_seg, out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}

@@ -1,0 +1,74 @@
+// Shared device helpers for the SSF-SLAM scene-flow front end kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SSF_OK 0
+#define SSF_ERR_ARG 1
+#define SSF_ERR_CUDA 2
+
+#define SSF_LAUNCH_CHECK()                                  \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return ssf_set_error(e__);  \
+    } while (0)
+
+int ssf_set_error(cudaError_t e);
+int ssf_arg_error(const char* msg);
+void ssf_count_launch();
+
+// Squared distance exactly as the written spec (mirrors
+// ASF/utils/utils.py:85,106): every multiply and add rounded to fp32, no FMA contraction.
+__device__ __forceinline__ float ssf_sqdist(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx);
+    float dy = __fsub_rn(ay, by);
+    float dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float ssf_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float ssf_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- mbarrier + bulk async copy (TMA engine, 1-D; SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ uint32_t ssf_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void ssf_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ssf_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ssf_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ssf_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ssf_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void ssf_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(ssf_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void ssf_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ssf_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(ssf_smem_u32(bar))
+                 : "memory");
+}

@@ -1,0 +1,104 @@
+"""Host-facing front end: the calls the reference's ROS drivers make after (or instead of) the network.
+
+Mirrors, with NumPy arrays in and out exactly like the reference's in-process code:
+
+* ``slove_RT_by_SVD(src, dst) -> (R[3,3], t[3,1])``  -- scripts/PointCloudOdometry.py:15-33 (same spelling);
+  computed on the GPU by the Kabsch reduction kernel (fp64 accumulators, Horn closed form) instead of
+  ``np.linalg.svd``.  The reflection branch returns the proper rotation the reference intended
+  (its ``Vt.T & U.T`` raises TypeError -- deliberate divergence).
+* ``background_index(points, flow, ...) -> bg_index`` -- stands where the drivers compute ``bg_index`` from the GMM
+  (ASF/main_sju_occ_ros.py:257-263) or the GT mask (scripts/PointCloudOdometry.py:91): the deterministic
+  residual-vs-rigid-flow masker with optional per-instance voting.
+* ``odometry(points, flow, ...)`` -- mask + pose + the ``frame_odom1`` payload ``[tx,ty,tz,qx,qy,qz,qw]`` in one launch.
+* ``SceneFlowFrontEnd`` -- network + mask + ego-motion for batches of frame pairs held in HOST memory (the end-to-end
+  call ``bench.py`` times: H2D of the clouds, all kernels, D2H of masks and poses).
+"""
+import numpy as np
+import torch
+
+from . import functional as F_
+from . import _native as nat
+
+
+def _dev(a, dtype, device):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+
+
+def slove_RT_by_SVD(src, dst, device="cuda:0"):
+    """Un-weighted rigid fit dst ~= R @ src + t over all rows; src, dst [M,3] array-likes -> (R [3,3], t [3,1]) float64."""
+    nat.require_device()
+    src_t = torch.from_numpy(np.ascontiguousarray(src, np.float32)).to(device).unsqueeze(0)
+    dst_t = torch.from_numpy(np.ascontiguousarray(dst, np.float32)).to(device).unsqueeze(0)
+    _, _, pose = F_.frontend(dst_t, src_t, mode=2, want_pose=True)
+    pose = pose[0].cpu().numpy()
+    return pose[:9].reshape(3, 3).copy(), pose[9:].reshape(3, 1).copy()
+
+
+def odometry(points, flow, mask=None, sem=None, inst=None, movable=(), tau=0.10, device="cuda:0"):
+    """points, flow [N,3] (or [B,N,3]) -> dict(mask u8, bg_index, odom f64[7] = [t, qx,qy,qz,qw], R, t).
+    ``mask`` given (0 = background, as ``s_fg_mask``) -> pose from those points only (GT-mask variants);
+    otherwise the residual masker runs (noSeg), seeded/voted by ``sem``/``inst`` when given (Seg)."""
+    nat.require_device()
+    p = np.asarray(points, np.float32)
+    single = p.ndim == 2
+    if single:
+        p = p[None]
+    f = np.asarray(flow, np.float32).reshape(p.shape)
+    tp, tf = _dev(p, torch.float32, device), _dev(f, torch.float32, device)
+    if mask is not None:
+        tm = _dev(np.asarray(mask).reshape(p.shape[:2]) != 0, torch.uint8, device)
+        m, odom, pose = F_.frontend(tp, tf, mode=0, in_mask=tm, want_pose=True)
+    else:
+        ts = None if sem is None else _dev(np.asarray(sem).reshape(p.shape[:2]), torch.int32, device)
+        ti = None if inst is None else _dev(np.asarray(inst).reshape(p.shape[:2]), torch.int32, device)
+        n_inst = 0 if inst is None else int(np.max(inst)) + 1
+        m, odom, pose = F_.frontend(tp, tf, mode=1, sem=ts, movable=movable, inst=ti, n_inst=n_inst, tau=tau, want_pose=True)
+    m, odom, pose = m.cpu().numpy(), odom.cpu().numpy(), pose.cpu().numpy()
+    out = dict(mask=m, odom=odom, R=pose[:, :9].reshape(-1, 3, 3), t=pose[:, 9:])
+    if single:
+        out = {k: v[0] for k, v in out.items()}
+        out["bg_index"] = np.flatnonzero(out["mask"] == 0)
+    return out
+
+
+def background_index(points, flow, sem=None, inst=None, movable=(), tau=0.10, device="cuda:0"):
+    """bg_index (ascending int64) of the static points, the quantity the drivers feed to slove_RT_by_SVD."""
+    return odometry(points, flow, sem=sem, inst=inst, movable=movable, tau=tau, device=device)["bg_index"]
+
+
+class SceneFlowFrontEnd:
+    """Scene flow + dynamic mask + ego-motion for batches of frame pairs in host memory."""
+
+    def __init__(self, net, device="cuda:0", tau=0.10, movable=()):
+        nat.require_device()
+        self.net, self.device, self.tau, self.movable = net, torch.device(device), tau, tuple(movable)
+        self._pin = {}
+
+    def _staged(self, name, arr, dtype):
+        """host array -> pinned staging buffer -> device (async on the current stream)."""
+        t = torch.as_tensor(arr)
+        key = (name, tuple(t.shape), dtype)
+        if key not in self._pin:
+            self._pin[key] = torch.empty(t.shape, dtype=dtype, pin_memory=True)
+        self._pin[key].copy_(t)
+        return self._pin[key].to(self.device, non_blocking=True)
+
+    @torch.no_grad()
+    def process(self, pos1, pos2, sem=None, inst=None, n_inst=0, return_flow=False):
+        """pos1, pos2: host f32 [B,N,3] -> dict(mask u8 [B,N], odom f64 [B,7] (, flow f32 [B,N,3])) on the host."""
+        x1 = self._staged("p1", pos1, torch.float32)
+        x2 = self._staged("p2", pos2, torch.float32)
+        ts = None if sem is None else self._staged("sem", sem, torch.int32)
+        ti = None if inst is None else self._staged("inst", inst, torch.int32)
+        flows, _ = self.net.forward_pm(x1, x2)
+        mask, odom = F_.frontend(x1, flows[0], mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
+        out = dict(mask=mask.cpu(), odom=odom.cpu())
+        if return_flow:
+            out["flow"] = flows[0].cpu()
+        return out
+
+    def h2d_bytes(self, B, N, seg=False):
+        return B * N * 3 * 4 * 2 + (B * N * 4 * 2 if seg else 0)
+
+    def d2h_bytes(self, B, N, return_flow=False):
+        return B * N + B * 7 * 8 + (B * N * 12 if return_flow else 0)

@@ -1,0 +1,143 @@
+"""Point-major functional layer of the fused path: thin Python over the C ABI (``include/ssf_b200.h``).
+
+Tensors are torch CUDA fp32 ``[B, N, C]`` (features) / ``[B, N, 3]`` (coordinates) / int32 ``[B, N, k]`` (indices);
+weights are K-major ``[Cin, Cout]`` (see ``ssf_slam_b200.model.prepare_weights``).  Every function is one kernel
+launch of ours on the current stream; nothing here computes with torch ops.
+"""
+import torch
+
+from . import _native as nat
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def _rows(x):
+    """Leading dims flattened: [..., C] contiguous -> (rows, C, ld)."""
+    assert x.is_contiguous() and x.dtype == torch.float32
+    return x.numel() // x.shape[-1], x.shape[-1], x.shape[-1]
+
+
+def linear(x1, Wt, cout, w_off1=0, x2=None, w_off2=0, bias=None, act=ACT_NONE, clamp1=0.0, add=None, clamp2=0.0):
+    """y[..., cout] = clamp2(clamp1(act(x1 @ Wt[w_off1:w_off1+C1] (+ x2 @ Wt[w_off2:...]) + bias)) + add)."""
+    rows, c1, ld1 = _rows(x1)
+    c2 = ld2 = 0
+    if x2 is not None:
+        r2, c2, ld2 = _rows(x2)
+        assert r2 == rows
+    assert Wt.is_contiguous() and Wt.shape[1] == cout
+    y = torch.empty(x1.shape[:-1] + (cout,), dtype=torch.float32, device=x1.device)
+    if add is not None:
+        assert add.is_contiguous() and add.shape[-1] == cout
+    nat.check(nat.lib().ssf_linear(nat.ptr(x1), c1, ld1, nat.ptr(x2), c2, ld2, nat.ptr(Wt), cout, w_off1, w_off2,
+                                   nat.ptr(bias), rows, cout, act, float(clamp1), nat.ptr(add), cout, float(clamp2),
+                                   nat.ptr(y), cout, nat.stream()))
+    return y
+
+
+def gather_rows(src, idx):
+    """src [B,N,C], idx i32 [B,M] -> [B,M,C]."""
+    B, N, C = src.shape
+    M = idx.shape[1]
+    out = torch.empty(B, M, C, dtype=torch.float32, device=src.device)
+    nat.check(nat.lib().ssf_gather_rows(nat.ptr(src), nat.ptr(idx), B, N, M, C, nat.ptr(out), nat.stream()))
+    return out
+
+
+def transpose(x):
+    """[B,R,C] -> [B,C,R] (contiguous)."""
+    B, R, C = x.shape
+    out = torch.empty(B, C, R, dtype=torch.float32, device=x.device)
+    nat.check(nat.lib().ssf_transpose(nat.ptr(x), B, R, C, nat.ptr(out), nat.stream()))
+    return out
+
+
+def fps(xyz, npoint):
+    B, N, _ = xyz.shape
+    out = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
+    nat.check(nat.lib().ssf_furthest_point_sample(nat.ptr(xyz), B, N, npoint, nat.ptr(out), nat.stream()))
+    return out
+
+
+def knn_idx(k, query, ref, offset=None):
+    """Indices only (every hot call site discards the distances): i32 [B,Nq,k]."""
+    B, Nq, _ = query.shape
+    Nr = ref.shape[1]
+    idx = torch.empty(B, Nq, k, dtype=torch.int32, device=query.device)
+    nat.check(nat.lib().ssf_knn_offset(k, nat.ptr(query), nat.ptr(offset), nat.ptr(ref), B, Nq, Nr, None, nat.ptr(idx),
+                                       nat.stream()))
+    return idx
+
+
+def interpolate(query, src_pos, src_val, idx, mode=0, clampv=100.0):
+    B, N, _ = query.shape
+    M, C = src_val.shape[1], src_val.shape[2]
+    k = idx.shape[2]
+    out = torch.empty(B, N, C, dtype=torch.float32, device=query.device)
+    nat.check(nat.lib().ssf_interpolate(nat.ptr(query), nat.ptr(src_pos), nat.ptr(src_val), nat.ptr(idx), B, N, M, C, k,
+                                        mode, float(clampv), nat.ptr(out), nat.stream()))
+    return out
+
+
+def group_mlp_max(G, idx, pos_src, pos_q, Wd, bias1, W2t, b2, C2, W3t=None, b3=None, C3=0, H=None, act=ACT_RELU):
+    """rows (n,s): x = act(G[idx] + H[n] + Wd.(pos_src[idx]-pos_q[n]) + bias1) -> dense layers -> max over s."""
+    B, Nsrc, C1 = G.shape
+    Nq, S = idx.shape[1], idx.shape[2]
+    clast = C3 if C3 > 0 else C2
+    out = torch.empty(B, Nq, clast, dtype=torch.float32, device=G.device)
+    nat.check(nat.lib().ssf_group_mlp_max(nat.ptr(G), nat.ptr(H), nat.ptr(bias1), nat.ptr(Wd), nat.ptr(pos_src),
+                                          nat.ptr(pos_q), nat.ptr(idx), nat.ptr(W2t), nat.ptr(b2), C2, nat.ptr(W3t),
+                                          nat.ptr(b3), C3, B, Nsrc, Nq, S, C1, act, nat.ptr(out), nat.stream()))
+    return out
+
+
+def cost_volume(Gab, Hab, w, H3, xyz1, xyz2, idx, idxw, m):
+    """Fused cost-volume core; ``w`` is the per-level dict from prepare_weights.  Returns
+    (cost_fwd [B,N1,m], cost_fwd_cm [B,m,N1], gw [B,N1*16], Cw [B,N1*16,m])."""
+    B, N1, _ = xyz1.shape
+    N2 = xyz2.shape[1]
+    dev = xyz1.device
+    cost_fwd = torch.empty(B, N1, m, dtype=torch.float32, device=dev)
+    cost_fwd_cm = torch.empty(B, m, N1, dtype=torch.float32, device=dev)
+    gw = torch.empty(B, N1 * 16, dtype=torch.float32, device=dev)
+    Cw = torch.empty(B, N1 * 16, m, dtype=torch.float32, device=dev)
+    p = nat.ptr
+    nat.check(nat.lib().ssf_cost_volume(p(Gab), p(Hab), p(w["W2a"]), p(w["b2a"]), p(w["W2w"]), p(w["b2w"]), p(w["W3a"]),
+                                        p(H3), p(w["W3d"]), p(w["W3b"]), p(w["b3b"]), p(w["Wn1"]), p(w["bn1"]), p(w["Wn2"]),
+                                        p(w["bn2"]), p(w["wn3"]), float(w["bn3"]), p(xyz1), p(xyz2), p(idx), p(idxw), B, N1,
+                                        N2, m, p(cost_fwd), p(cost_fwd_cm), p(gw), p(Cw), nat.stream()))
+    return cost_fwd, cost_fwd_cm, gw, Cw
+
+
+def build_csr(key, n_seg):
+    """key i32/i64 [B,L] -> workspace tensor describing, per segment, its rows in ascending order."""
+    B, L = key.shape
+    ws = torch.empty(int(nat.lib().ssf_csr_workspace_ints(B, L, n_seg)), dtype=torch.int32, device=key.device)
+    fn = nat.lib().ssf_build_csr_i64 if key.dtype == torch.int64 else nat.lib().ssf_build_csr_i32
+    nat.check(fn(nat.ptr(key), B, L, n_seg, nat.ptr(ws), nat.stream()))
+    return ws
+
+
+def segment_softmax_sum(logit, val, csr, n_seg):
+    """logit [B,L], val [B,L,C] -> [B,n_seg,C] (zeros for empty segments)."""
+    B, L, C = val.shape
+    out = torch.empty(B, n_seg, C, dtype=torch.float32, device=val.device)
+    nat.check(nat.lib().ssf_segment_softmax_sum(nat.ptr(logit), nat.ptr(val), nat.ptr(csr), B, L, C, n_seg, nat.ptr(out),
+                                                nat.stream()))
+    return out
+
+
+def frontend(points, flow, mode=1, in_mask=None, sem=None, movable=(), inst=None, n_inst=0, tau=0.10, want_pose=False):
+    """points, flow f32 [B,N,3] -> (mask u8 [B,N], odom f64 [B,7] (, pose f64 [B,12]))."""
+    B, N, _ = points.shape
+    dev = points.device
+    mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    odom = torch.empty(B, 7, dtype=torch.float64, device=dev)
+    pose = torch.empty(B, 12, dtype=torch.float64, device=dev) if want_pose else None
+    bits = 0
+    for c in movable:
+        if 0 <= int(c) < 64:
+            bits |= 1 << int(c)
+    nat.check(nat.lib().ssf_frontend(nat.ptr(points), nat.ptr(flow), B, N, mode, nat.ptr(in_mask), nat.ptr(sem), bits,
+                                     nat.ptr(inst), int(n_inst), float(tau), nat.ptr(mask), nat.ptr(odom), nat.ptr(pose),
+                                     nat.stream()))
+    return (mask, odom, pose) if want_pose else (mask, odom)

@@ -1,0 +1,369 @@
+"""B200-native ActiveSceneFlow ``TFlow`` with the reference's call surface.
+
+``TFlow(npoint=8192)`` / ``forward(pc1[B,3,N], pc2[B,3,N]) -> ([flow B x3xN, B x3x2048, B x3x512, B x3x256],
+[fps idx B x2048, B x512, B x256])`` exactly as ``ASF/TFlowV3_Occlussion.py:65-196``, and the module tree exposes
+the same ``state_dict`` keys (317 tensors), so the reference's checkpoint (``model.best.t7``, loaded at
+``ASF/main_sju_occ_ros.py:698-711``, also under ``nn.DataParallel``'s ``module.`` prefix) loads with
+``strict=True``.  The torch modules below are parameter holders only: ``forward`` never runs a torch op on the
+hot path; it folds eval-mode BatchNorm, re-lays the weights K-major once, and drives the fused sm_100a kernels
+(``ssf_slam_b200.functional``).  Inference / eval mode only, as in the reference's ROS drivers.
+
+Structure of the forward (what the reference does per level, re-expressed point-major and fused):
+  pyramid   : FPS -> kNN -> [gather -> 3x(conv+BN+ReLU) -> max]           ASF/utils/utils.py:208-248
+  up-conv   : kNN -> [gather -> 2x(conv+BN+ReLU) -> max] -> 2x linear      ASF/utils/utils.py:274-315
+  regressor : warp -> 2x kNN -> fused cost volume -> segmented softmax/sum -> [gather -> mlp_convs4 -> max]
+              -> flow head                                                  ASF/utils/soflow.py:354-525,1223-1257
+  upsample  : kNN / 3-NN -> inverse-distance interpolation                  ASF/utils/soflow.py:1443-1475
+Both clouds of a pair travel through the pyramid and the up-convs as one batch of 2B clouds.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from . import _native as nat
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = F_.ACT_NONE, F_.ACT_RELU, F_.ACT_LEAKY
+
+
+# --------------------------------------------------------------------------- parameter holders
+# (names mirror the reference module tree so that state_dict keys are identical)
+
+class _LeakyConv1d(nn.Module):
+    """`Conv1d` blocks: `.composed_module.0` is the conv (ASF/TFlowV3_Occlussion.py:22-38 no bias;
+    ASF/utils/soflow.py:1260-1276 with bias)."""
+
+    def __init__(self, cin, cout, bias):
+        super().__init__()
+        self.composed_module = nn.Sequential(nn.Conv1d(cin, cout, 1, bias=bias), nn.Identity(), nn.Identity())
+
+
+class PointNetSetAbstraction(nn.Module):
+    """Parameters of ASF/utils/utils.py:185-201 (radius / group_all are accepted and ignored, as there)."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all=False):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel + 3
+        for c in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, c, 1, bias=False))
+            self.mlp_bns.append(nn.BatchNorm2d(c))
+            last = c
+
+
+class PointNetSetUpConv(nn.Module):
+    """Parameters of ASF/utils/utils.py:250-272."""
+
+    def __init__(self, nsample, radius, f1_channel, f2_channel, mlp, mlp2, knn=True):
+        super().__init__()
+        self.nsample, self.radius, self.knn = nsample, radius, knn
+        self.mlp1_convs = nn.ModuleList()
+        self.mlp2_convs = nn.ModuleList()
+        last = f2_channel + 3
+        for c in mlp:
+            self.mlp1_convs.append(nn.Sequential(nn.Conv2d(last, c, 1, bias=False), nn.BatchNorm2d(c), nn.ReLU()))
+            last = c
+        last = (mlp[-1] if len(mlp) else last) + f1_channel
+        for c in mlp2:
+            self.mlp2_convs.append(nn.Sequential(nn.Conv1d(last, c, 1, bias=False), nn.BatchNorm1d(c), nn.ReLU()))
+            last = c
+
+
+class PointConvTransFlowV2(nn.Module):
+    """Parameters of ASF/utils/soflow.py:281-346 (bn=False, 3-channel flow head)."""
+
+    def __init__(self, nsample, in_channel, sf_channel, mlp, flow_mlp, use_flow=True):
+        super().__init__()
+        self.nsample, self.use_flow = nsample, use_flow
+        self.in_channel, self.sf_channel, self.mlp, self.flow_mlp = in_channel, sf_channel, list(mlp), list(flow_mlp)
+        m = mlp[-1]
+
+        def stack(cin):
+            ml = nn.ModuleList()
+            for c in mlp:
+                ml.append(nn.Conv2d(cin, c, 1))
+                cin = c
+            return ml
+
+        self.mlp_convs = stack(in_channel * 2)
+        self.mlp_convs2 = stack(in_channel * 2)
+        self.weightnet1 = nn.Sequential(nn.Conv2d(m, m, 1, bias=False), nn.BatchNorm2d(m), nn.ReLU(),
+                                        nn.Conv2d(m, m // 2, 1, bias=False), nn.BatchNorm2d(m // 2), nn.ReLU(),
+                                        nn.Conv2d(m // 2, 1, 1))
+        self.mlp_convs3 = stack(m + sf_channel + 3)
+        self.mlp_convs4 = stack(m * 2 + sf_channel + 3)
+        self.flow_mlp_convs = nn.ModuleList()
+        last = m
+        for c in flow_mlp:
+            self.flow_mlp_convs.append(_LeakyConv1d(last, c, bias=True))
+            last = c
+        self.fc = nn.Conv1d(last, 3, 1)
+
+
+class RefineFlowRegressor(nn.Module):
+    """ASF/TFlowV3_Occlussion.py:41-49: `.cost` holds the cost volume; `.warping` has no parameters."""
+
+    def __init__(self, nsample, in_channel, feat_channel, mlp, flow_mlp, use_flow=True):
+        super().__init__()
+        self.use_flow, self.nsample = use_flow, nsample
+        self.cost = PointConvTransFlowV2(nsample, in_channel, feat_channel, mlp, flow_mlp, use_flow=use_flow)
+
+
+# ------------------------------------------------------------------------------ weight preparation
+
+def _fold_bn(w2d, bn, prefix, sd):
+    """conv (no bias) + eval BatchNorm -> (W', b') with W' [Cout, Cin]."""
+    g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
+    mu, var = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
+    scale = g / torch.sqrt(var + bn)
+    return (w2d.double() * scale[:, None]).float(), (b - mu * scale).float()
+
+
+def _kmajor(w2d):
+    return w2d.t().contiguous()
+
+
+def prepare_weights(state_dict, device):
+    """Reference-format state_dict -> dict of K-major, BN-folded fp32 device tensors used by the kernels."""
+    sd = {k[7:] if k.startswith("module.") else k: v.detach().to("cpu") for k, v in state_dict.items()}
+    W = {}
+    eps = 1e-5
+
+    def w2(key):
+        w = sd[key]
+        return w.reshape(w.shape[0], w.shape[1]).float()
+
+    def dev(t):
+        return t.contiguous().to(device)
+
+    W["pc0"] = dev(_kmajor(w2("point_conv.0.composed_module.0.weight")))
+    W["pc1"] = dev(_kmajor(w2("point_conv.1.composed_module.0.weight")))
+    for name in ("deconv3_2", "deconv2_1", "deconv1_0"):
+        W[name] = dev(_kmajor(w2(name + ".composed_module.0.weight")))
+
+    for name in ("sa1", "sa2", "sa3", "sa4"):
+        layers = []
+        i = 0
+        while "%s.mlp_convs.%d.weight" % (name, i) in sd:
+            w, b = _fold_bn(w2("%s.mlp_convs.%d.weight" % (name, i)), eps, "%s.mlp_bns.%d" % (name, i), sd)
+            layers.append((w, b))
+            i += 1
+        assert len(layers) == 3
+        w1, b1 = layers[0]
+        W[name] = dict(Wd=dev(_kmajor(w1[:, :3])), Wg=dev(_kmajor(w1[:, 3:])), b1=dev(b1),
+                       W2=dev(_kmajor(layers[1][0])), b2=dev(layers[1][1]), C2=layers[1][0].shape[0],
+                       W3=dev(_kmajor(layers[2][0])), b3=dev(layers[2][1]), C3=layers[2][0].shape[0], C1=w1.shape[0])
+
+    for name in ("su3", "su2", "su1", "su0"):
+        m1 = []
+        i = 0
+        while "%s.mlp1_convs.%d.0.weight" % (name, i) in sd:
+            m1.append(_fold_bn(w2("%s.mlp1_convs.%d.0.weight" % (name, i)), eps, "%s.mlp1_convs.%d.1" % (name, i), sd))
+            i += 1
+        m2 = []
+        i = 0
+        while "%s.mlp2_convs.%d.0.weight" % (name, i) in sd:
+            m2.append(_fold_bn(w2("%s.mlp2_convs.%d.0.weight" % (name, i)), eps, "%s.mlp2_convs.%d.1" % (name, i), sd))
+            i += 1
+        assert len(m1) == 2 and len(m2) == 2
+        w1, b1 = m1[0]
+        c2 = w1.shape[1] - 3
+        W[name] = dict(Wg=dev(_kmajor(w1[:, :c2])), Wd=dev(_kmajor(w1[:, c2:])), b1=dev(b1), C1=w1.shape[0],
+                       W2=dev(_kmajor(m1[1][0])), b2=dev(m1[1][1]), C2=m1[1][0].shape[0],
+                       M1=dev(_kmajor(m2[0][0])), mb1=dev(m2[0][1]), MC1=m2[0][0].shape[0],
+                       M2=dev(_kmajor(m2[1][0])), mb2=dev(m2[1][1]), MC2=m2[1][0].shape[0])
+
+    for name in ("flow3_r", "flow2_r", "flow1_r", "flow0_r"):
+        p = name + ".cost"
+        wa, ba = w2(p + ".mlp_convs.0.weight"), sd[p + ".mlp_convs.0.bias"].float()
+        ww, bw = w2(p + ".mlp_convs2.0.weight"), sd[p + ".mlp_convs2.0.bias"].float()
+        m, D = wa.shape[0], wa.shape[1] // 2
+        w3, b3 = w2(p + ".mlp_convs3.0.weight"), sd[p + ".mlp_convs3.0.bias"].float()
+        Fc = w3.shape[1] - m - 3
+        w4, b4 = w2(p + ".mlp_convs4.0.weight"), sd[p + ".mlp_convs4.0.bias"].float()
+        wn1, bn1 = _fold_bn(w2(p + ".weightnet1.0.weight"), eps, p + ".weightnet1.1", sd)
+        wn2, bn2 = _fold_bn(w2(p + ".weightnet1.3.weight"), eps, p + ".weightnet1.4", sd)
+        d = dict(m=m, D=D, F=Fc,
+                 Wab=dev(torch.cat([_kmajor(wa), _kmajor(ww)], dim=1)),       # [2D, 2m]; rows [0,D) per-query, [D,2D) gathered
+                 bab=dev(torch.cat([ba, bw])),
+                 W2a=dev(_kmajor(w2(p + ".mlp_convs.1.weight"))), b2a=dev(sd[p + ".mlp_convs.1.bias"].float()),
+                 W2w=dev(_kmajor(w2(p + ".mlp_convs2.1.weight"))), b2w=dev(sd[p + ".mlp_convs2.1.bias"].float()),
+                 W3=dev(_kmajor(w3)), b3=dev(b3),                              # rows [0,m) A | [m,m+F) sf_feat | [m+F,m+F+3) dir
+                 W3b=dev(_kmajor(w2(p + ".mlp_convs3.1.weight"))), b3b=dev(sd[p + ".mlp_convs3.1.bias"].float()),
+                 Wn1=dev(_kmajor(wn1)), bn1=dev(bn1), Wn2=dev(_kmajor(wn2)), bn2=dev(bn2),
+                 wn3=dev(w2(p + ".weightnet1.6.weight").reshape(-1)), bn3=float(sd[p + ".weightnet1.6.bias"].reshape(-1)[0]),
+                 W4=dev(_kmajor(w4)), b4=dev(b4),                              # rows [0,m) fwd | [m,2m) bwd | [2m,2m+F) sf_feat | dir
+                 W42=dev(_kmajor(w2(p + ".mlp_convs4.1.weight"))), b42=dev(sd[p + ".mlp_convs4.1.bias"].float()),
+                 fc=dev(_kmajor(w2(p + ".fc.weight"))), fcb=dev(sd[p + ".fc.bias"].float()))
+        d["W3a"] = d["W3"][:m]
+        d["W3d"] = d["W3"][m + Fc:]
+        d["W4d"] = d["W4"][2 * m + Fc:]
+        fm = []
+        i = 0
+        while "%s.flow_mlp_convs.%d.composed_module.0.weight" % (p, i) in sd:
+            k = "%s.flow_mlp_convs.%d.composed_module.0" % (p, i)
+            fm.append((dev(_kmajor(w2(k + ".weight"))), dev(sd[k + ".bias"].float()), sd[k + ".weight"].shape[0]))
+            i += 1
+        d["flow_mlp"] = fm
+        W[name] = d
+    return W
+
+
+# ------------------------------------------------------------------------------ point-major forward pieces
+
+def set_abstraction_pm(w, npoint, nsample, xyz, feats):
+    """xyz [B,N,3], feats [B,N,D] -> (new_xyz [B,S,3], new_feats [B,S,C3], fps_idx [B,S])."""
+    fps_idx = F_.fps(xyz, npoint)
+    new_xyz = F_.gather_rows(xyz, fps_idx)
+    idx = F_.knn_idx(nsample, new_xyz, xyz)
+    G = F_.linear(feats, w["Wg"], w["C1"])
+    out = F_.group_mlp_max(G, idx, xyz, new_xyz, w["Wd"], w["b1"], w["W2"], w["b2"], w["C2"], w["W3"], w["b3"], w["C3"],
+                           act=ACT_RELU)
+    return new_xyz, out, fps_idx
+
+
+def set_upconv_pm(w, nsample, pos1, pos2, feat1, feat2):
+    """Feature propagation sparse (pos2, feat2) -> dense (pos1, feat1): [B,N1,mlp2[-1]]."""
+    idx = F_.knn_idx(nsample, pos1, pos2)
+    G = F_.linear(feat2, w["Wg"], w["C1"])
+    pooled = F_.group_mlp_max(G, idx, pos2, pos1, w["Wd"], w["b1"], w["W2"], w["b2"], w["C2"], act=ACT_RELU)
+    x = F_.linear(pooled, w["M1"], w["MC1"], 0, feat1, w["C2"], bias=w["mb1"], act=ACT_RELU)
+    return F_.linear(x, w["M2"], w["MC2"], bias=w["mb2"], act=ACT_RELU)
+
+
+def upsample_pm(xyz, sparse_xyz, sparse_val, k=3):
+    """UpsampleFlow: [B,S,C] on sparse_xyz -> [B,N,C] on xyz."""
+    idx = F_.knn_idx(k, xyz, sparse_xyz)
+    return F_.interpolate(xyz, sparse_xyz, sparse_val, idx, mode=0, clampv=100.0)
+
+
+def point_warping_pm(pos1, pos2, flow1, k):
+    """PointWarping: pos2 pulled back by the flow interpolated from pos1 + flow1 (positions clamped to +-10 m)."""
+    moved = pos1 + flow1  # one rounded fp32 add per coordinate, as `pos1 + flow1` at soflow.py:1231 (glue, 3 floats/point)
+    idx = F_.knn_idx(3 if k is None else k, pos2, moved)
+    return F_.interpolate(pos2, moved, flow1, idx, mode=1, clampv=10.0)
+
+
+def cost_volume_pm(w, xyz1, xyz2, xyz2w, f1a, f1b, f2a, f2b, sf=None, sf_feat=None):
+    """PointConvTransFlowV2 on point-major inputs.  f1 = cat[f1a | f1b], f2 = cat[f2a | f2b] (b parts may be None).
+    Returns (cost_fwd [B,N1,m], cost_bwd [B,N2,m], feats [B,N1,flow_mlp[-1]], flow [B,N1,3])."""
+    m, D, Fc = w["m"], w["D"], w["F"]
+    B, N1, _ = xyz1.shape
+    N2 = xyz2.shape[1]
+    ca = f1a.shape[-1]
+    idx = F_.knn_idx(16, xyz1, xyz2, offset=sf)
+    idxw = F_.knn_idx(16, xyz1, xyz2 if xyz2w is None else xyz2w)
+    Hab = F_.linear(f1a, w["Wab"], 2 * m, 0, f1b, ca, bias=w["bab"])
+    Gab = F_.linear(f2a, w["Wab"], 2 * m, D, f2b, D + ca)
+    if Fc > 0:
+        H3 = F_.linear(sf_feat, w["W3"], m, m, bias=w["b3"])
+    else:
+        H3 = w["b3"].view(1, 1, m).expand(B, N1, m).contiguous()
+    cost_fwd, cost_fwd_cm, gw, Cw = F_.cost_volume(Gab, Hab, w, H3, xyz1, xyz2, idx, idxw, m)
+    csr = F_.build_csr(idxw.view(B, N1 * 16), N2)
+    cost_bwd = F_.segment_softmax_sum(gw, Cw, csr, N2)
+    # mlp_convs4 input = cat[scrambled fwd | bwd[idx] | sf_feat | dir]; the "scramble" is the reference's .view of
+    # the channel-major forward cost as [N1, m] rows (soflow.py:490): reinterpret, do not transpose
+    scr = cost_fwd_cm.view(B, N1, m)
+    if Fc > 0:
+        Hp = F_.linear(scr, w["W4"], m, 0, sf_feat, 2 * m, bias=w["b4"])
+    else:
+        Hp = F_.linear(scr, w["W4"], m, 0, bias=w["b4"])
+    G4 = F_.linear(cost_bwd, w["W4"], m, m)
+    x = F_.group_mlp_max(G4, idx, xyz2, xyz1, w["W4d"], None, w["W42"], w["b42"], m, H=Hp, act=ACT_LEAKY)
+    for Wt, b, c in w["flow_mlp"]:
+        x = F_.linear(x, Wt, c, bias=b, act=ACT_LEAKY)
+    flow = F_.linear(x, w["fc"], 3, bias=w["fcb"], clamp1=50.0, add=sf, clamp2=50.0)
+    return cost_fwd, cost_bwd, x, flow
+
+
+# ------------------------------------------------------------------------------------- the model
+
+class TFlow(nn.Module):
+    """Drop-in for ``TFlowV3_Occlussion.TFlow`` (same ctor, forward signature, outputs and state_dict keys)."""
+
+    SA = (("sa1", 2048, 16), ("sa2", 512, 16), ("sa3", 256, 16), ("sa4", 128, 8))
+
+    def __init__(self, npoint=8192):
+        super().__init__()
+        self.point_conv = nn.Sequential(_LeakyConv1d(3, 32, bias=False), _LeakyConv1d(32, 32, bias=False))
+        self.sa1 = PointNetSetAbstraction(2048, 0.5, 16, 32, [32, 32, 64])
+        self.sa2 = PointNetSetAbstraction(512, 2.0, 16, 64, [64, 64, 128])
+        self.sa3 = PointNetSetAbstraction(256, 4.0, 16, 128, [128, 128, 256])
+        self.sa4 = PointNetSetAbstraction(128, 8.0, 8, 256, [256, 256, 512])
+        self.su3 = PointNetSetUpConv(16, 2.4, 256, 512, [256, 256], [256, 256])
+        self.flow3_r = RefineFlowRegressor(16, 256, 0, [256, 256], [128, 128], use_flow=False)
+        self.su2 = PointNetSetUpConv(16, 2.4, 128, 256, [128, 128], [128, 128])
+        self.flow2_r = RefineFlowRegressor(16, 128 + 64, 128, [128, 128], [128, 128])
+        self.su1 = PointNetSetUpConv(16, 2.4, 64, 128, [64, 64], [64, 64])
+        self.flow1_r = RefineFlowRegressor(16, 64 + 32, 128, [64, 64], [64, 64])
+        self.su0 = PointNetSetUpConv(16, 2.4, 32, 64, [64, 64], [64, 64])
+        self.flow0_r = RefineFlowRegressor(16, 64 + 32, 64, [64, 64], [64, 64])
+        self.deconv3_2 = _LeakyConv1d(256, 64, bias=False)
+        self.deconv2_1 = _LeakyConv1d(128, 32, bias=False)
+        self.deconv1_0 = _LeakyConv1d(64, 32, bias=False)
+        self._prepared = None
+        self.eval()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._prepared = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._prepared = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def weights(self, device):
+        if self._prepared is None or self._prepared[0] != device:
+            self._prepared = (device, prepare_weights(self.state_dict(), device))
+        return self._prepared[1]
+
+    @torch.no_grad()
+    def forward_pm(self, xyz1, xyz2):
+        """xyz1, xyz2 f32 [B,N,3] (point-major, CUDA) -> (flows pm [[B,N,3],[B,2048,3],[B,512,3],[B,256,3]], fps idx x3)."""
+        nat.require_device()
+        W = self.weights(xyz1.device)
+        B = xyz1.shape[0]
+        xyz = [torch.cat([xyz1, xyz2], dim=0).contiguous()]  # both clouds as one batch of 2B
+        x = F_.linear(xyz[0], W["pc0"], 32, act=ACT_LEAKY)
+        feats = [F_.linear(x, W["pc1"], 32, act=ACT_LEAKY)]
+        fps = []
+        for name, npoint, nsample in self.SA:
+            nx, nf, fi = set_abstraction_pm(W[name], npoint, nsample, xyz[-1], feats[-1])
+            xyz.append(nx), feats.append(nf), fps.append(fi)
+
+        def h1(t):
+            return t[:B]
+
+        def h2(t):
+            return t[B:]
+
+        up = set_upconv_pm(W["su3"], 16, xyz[3], xyz[4], feats[3], feats[4])
+        cf, cb, ff, flow = cost_volume_pm(W["flow3_r"], h1(xyz[3]), h2(xyz[3]), None, h1(up), None, h2(up), None)
+        flows = [flow]
+        for lvl, su, fr, dc, k_up, k_warp in ((2, "su2", "flow2_r", "deconv3_2", 5, 5), (1, "su1", "flow1_r", "deconv2_1", 5, 7),
+                                             (0, "su0", "flow0_r", "deconv1_0", 7, 7)):
+            up = set_upconv_pm(W[su], 16, xyz[lvl], xyz[lvl + 1], feats[lvl], up)
+            p1, p1s = h1(xyz[lvl]), h1(xyz[lvl + 1])
+            p2 = h2(xyz[lvl])
+            coarse = upsample_pm(p1, p1s, flow, k_up)
+            sf_feat = upsample_pm(p1, p1s, ff, k_up)
+            dcout = W[dc].shape[1]
+            cfu = F_.linear(upsample_pm(p1, p1s, cf, 3), W[dc], dcout, act=ACT_LEAKY)
+            cbu = F_.linear(upsample_pm(p1, p1s, cb, 3), W[dc], dcout, act=ACT_LEAKY)
+            warped = point_warping_pm(p1, p2, coarse, k_warp)
+            cf, cb, ff, flow = cost_volume_pm(W[fr], p1, p2, warped, h1(up), cfu, h2(up), cbu, sf=coarse, sf_feat=sf_feat)
+            flows.append(flow)
+        return flows[::-1], [f[:B] for f in fps[:3]]
+
+    @torch.no_grad()
+    def forward(self, pc1, pc2, feats1=None, feats2=None):
+        """Reference signature: pc1, pc2 f32 [B,3,N] CUDA -> ([4 flows B x3xn], [3 fps idx])."""
+        if feats1 is not None or feats2 is not None:
+            raise nat.SsfError("extra input features are not supported (the reference drivers never pass them)")
+        nat.require_device()
+        x1 = F_.transpose(pc1.contiguous().float())
+        x2 = F_.transpose(pc2.contiguous().float())
+        flows, fps = self.forward_pm(x1, x2)
+        return [F_.transpose(f) for f in flows], fps

@@ -62,7 +62,7 @@ class Street:
 
 def _ray_dirs():
     elev = np.deg2rad(np.linspace(-25.0, 5.0, 64))
-    azim = np.linspace(-np.pi, np.pi, 1800, endpoint=False)
+    azim = np.linspace(-np.pi, np.pi, 1024, endpoint=False)
     e, a = np.meshgrid(elev, azim, indexing="ij")
     return np.stack([np.cos(e) * np.cos(a), np.cos(e) * np.sin(a), np.sin(e)], -1).reshape(-1, 3)
 
@@ -131,10 +131,10 @@ def _subsample(rng, m, n):
     return rng.choice(m, n, replace=(m < n))
 
 
-def frame_pair(scene, f, n_points, rng):
+def frame_pair(scene, f, n_points, rng, scan1=None, scan2=None):
     """One npz-shaped item: dict(pos1,pos2,gt,ego_flow,s_fg_mask,t_fg_mask,sem,inst), fp32 / int."""
-    p1, sem1, inst1, veh1 = _scan(scene, f, rng)
-    p2, _, _, veh2 = _scan(scene, f + 1, rng)
+    p1, sem1, inst1, veh1 = scan1 if scan1 is not None else _scan(scene, f, rng)
+    p2, _, _, veh2 = scan2 if scan2 is not None else _scan(scene, f + 1, rng)
     i1 = _subsample(rng, len(p1), n_points)
     i2 = _subsample(rng, len(p2), n_points)
     p1, sem1, inst1, veh1 = p1[i1], sem1[i1], inst1[i1], veh1[i1]
@@ -156,10 +156,22 @@ def frame_pair(scene, f, n_points, rng):
 
 
 def make_sequence(seed, n_frames, n_points):
-    """List of n_frames frame-pair dicts along one trajectory (BASELINE.json configs 2-4)."""
+    """List of n_frames frame-pair dicts along one trajectory (BASELINE.json configs 2-4).  Every frame is
+    ray-cast once; pair f uses scan f (subsampled) as pos1 and scan f+1 (subsampled independently) as pos2."""
     scene = Street(seed, n_frames)
     rng = np.random.default_rng(seed + 7919)
-    return [frame_pair(scene, f, n_points, rng) for f in range(n_frames)]
+    scans = {}
+
+    def scan(f):
+        if f not in scans:
+            scans[f] = _scan(scene, f, rng)
+        return scans[f]
+
+    out = []
+    for f in range(n_frames):
+        out.append(frame_pair(scene, f, n_points, rng, scan(f), scan(f + 1)))
+        scans.pop(f, None)
+    return out
 
 
 def make_pair(seed, n_points):

@@ -1,0 +1,75 @@
+"""GPU parity: dynamic mask (bit-exact) + ego-motion vs the oracle spec and the reference's own pose function."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import frontend as ofe  # noqa: E402  (checker only)
+
+
+def test_masker_golden_bit_exact(golden_dir):
+    from ssf_slam_b200 import frontend
+    g = np.load(os.path.join(golden_dir, "masker.npz"))
+    a = frontend.odometry(g["pos1"], g["flow"], tau=0.10)
+    assert np.array_equal(a["mask"], g["mask_noseg"])
+    assert np.array_equal(a["odom"], g["odom_noseg"])  # fp64 pose bit-identical to the oracle spec
+    b = frontend.odometry(g["pos1"], g["flow"], sem=g["sem"], inst=g["inst"], movable=(2,), tau=0.10)
+    assert np.array_equal(b["mask"], g["mask_seg"])
+    assert np.array_equal(b["odom"], g["odom_seg"])
+    assert np.array_equal(a["bg_index"], np.flatnonzero(g["mask_noseg"] == 0))
+
+
+@pytest.mark.parametrize("n,seed", [(8192, 0), (16384, 1), (1000, 2), (257, 3), (3, 4), (2, 5)])
+def test_masker_random_vs_spec(n, seed):
+    from ssf_slam_b200 import frontend
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(-60, 60, (n, 3)).astype(np.float32)
+    yaw = 0.02
+    R = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    f = (p @ R.T + np.array([0.9, 0.05, 0.0]) - p + 0.02 * rng.standard_normal((n, 3))).astype(np.float32)
+    inst = rng.integers(0, 12, n).astype(np.int32)
+    sem = np.where(inst > 6, 2, 0).astype(np.int32)
+    mover = inst == 9
+    f[mover] += np.array([1.5, 0.0, 0.0], np.float32)
+    want = ofe.masker_spec(p, f, 0.1, sem=sem, inst=inst, movable=(2,))
+    got = frontend.odometry(p, f, sem=sem, inst=inst, movable=(2,), tau=0.1)
+    assert np.array_equal(got["mask"], want["mask"])
+    assert np.array_equal(got["odom"], want["odom"])
+    want = ofe.masker_spec(p, f, 0.1)
+    got = frontend.odometry(p, f, tau=0.1)
+    assert np.array_equal(got["mask"], want["mask"]) and np.array_equal(got["odom"], want["odom"])
+
+
+def test_gt_mask_pose_matches_reference_function(golden_dir):
+    """GT-mask variant (scripts/PointCloudOdometry.py:91-101): pose from the bg points vs slove_RT_by_SVD restated."""
+    from ssf_slam_b200 import frontend
+    g = np.load(os.path.join(golden_dir, "masker.npz"))
+    out = frontend.odometry(g["pos1"], g["flow"], mask=g["s_fg_mask"])
+    bg = ofe.gt_background(g["s_fg_mask"])
+    R, t = ofe.reference_pose(g["pos1"], g["flow"], bg)
+    assert np.allclose(out["R"], R, atol=1e-5) and np.allclose(out["t"], t.ravel(), atol=1e-4)
+    ref_msg = ofe.odom_message(R, t)
+    q_ok = min(np.abs(out["odom"][3:] - ref_msg[3:]).max(), np.abs(out["odom"][3:] + ref_msg[3:]).max())
+    assert q_ok < 1e-5 and np.abs(out["odom"][:3] - ref_msg[:3]).max() < 1e-4
+
+
+def test_slove_rt_by_svd_dropin(golden_dir):
+    from ssf_slam_b200 import frontend
+    g = np.load(os.path.join(golden_dir, "solve_rt.npz"))
+    R, t = frontend.slove_RT_by_SVD(g["src"], g["dst"])
+    assert R.shape == (3, 3) and t.shape == (3, 1)
+    assert np.allclose(R, g["R"], atol=1e-6) and np.allclose(t, g["t"], atol=1e-5)
+
+
+def test_batched_frontend_equals_single():
+    from ssf_slam_b200 import functional as F_
+    rng = np.random.default_rng(1)
+    p = rng.uniform(-50, 50, (4, 4096, 3)).astype(np.float32)
+    f = (0.5 + 0.05 * rng.standard_normal(p.shape)).astype(np.float32)
+    m, o = F_.frontend(torch.from_numpy(p).cuda(), torch.from_numpy(f).cuda(), mode=1, tau=0.1)
+    for b in range(4):
+        want = ofe.masker_spec(p[b], f[b], 0.1)
+        assert np.array_equal(m[b].cpu().numpy(), want["mask"]) and np.array_equal(o[b].cpu().numpy(), want["odom"])

@@ -1,0 +1,174 @@
+"""GPU parity: fused layers (teacher-forced against the oracle port's intermediates) and the whole TFlow forward
+against the committed reference goldens.  Tolerances: FPS / kNN indices exact; flow max-abs <= 1e-4 m (north star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import point_ops as po  # noqa: E402  (checker only)
+from oracle import tflow_port as tp  # noqa: E402  (checker only)
+
+FLOW_TOL = 1e-4
+
+
+def _pm(x):  # [B,C,N] cpu -> [B,N,C] cuda
+    return x.permute(0, 2, 1).contiguous().cuda()
+
+
+def _cm(x):  # [B,N,C] cuda -> [B,C,N] cpu
+    return x.permute(0, 2, 1).contiguous().cpu()
+
+
+@pytest.fixture(scope="module")
+def setup(golden_dir, oracle_c):
+    from ssf_slam_b200.model import TFlow, prepare_weights
+    g = np.load(os.path.join(golden_dir, "tflow_n2048.npz"))
+    sd = tp.random_init_state_dict(int(g["weight_seed"]))
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0)
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0)
+    (flows, fps), inter = tp.tflow_forward(sd, pc1, pc2, return_intermediates=True)
+    net = TFlow()
+    net.load_state_dict(sd, strict=True)
+    W = prepare_weights(sd, torch.device("cuda:0"))
+    return dict(g=g, sd=sd, pc1=pc1, pc2=pc2, flows=flows, fps=fps, inter=inter, net=net, W=W)
+
+
+def test_linear_matches_conv1d(setup):
+    from ssf_slam_b200 import functional as F_
+    sd, W = setup["sd"], setup["W"]
+    x = setup["pc1"]
+    want = tp.leaky_conv1d(sd, "point_conv.1", tp.leaky_conv1d(sd, "point_conv.0", x))
+    got = F_.linear(F_.linear(_pm(x), W["pc0"], 32, act=2), W["pc1"], 32, act=2)
+    assert float((_cm(got) - want).abs().max()) < 1e-5
+    assert float((_cm(got) - setup["inter"]["f1"][0]).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("lvl", [1, 2, 3, 4])
+def test_set_abstraction_teacher_forced(setup, lvl):
+    from ssf_slam_b200.model import set_abstraction_pm
+    name, npoint, nsample = tp.SA_CFG[lvl - 1]
+    inter = setup["inter"]
+    xyz, feats = inter["pcs1"][lvl - 1], inter["f1"][lvl - 1]
+    nx, nf, fi = set_abstraction_pm(setup["W"][name], npoint, nsample, _pm(xyz), _pm(feats))
+    assert torch.equal(fi.cpu(), inter["fps"][lvl - 1])
+    assert torch.equal(_cm(nx), inter["pcs1"][lvl])
+    err = float((_cm(nf) - inter["f1"][lvl]).abs().max())
+    assert err < 2e-5 * max(1.0, float(inter["f1"][lvl].abs().max())), err
+
+
+@pytest.mark.parametrize("lvl,name", [(3, "su3")])
+def test_set_upconv_teacher_forced(setup, lvl, name):
+    from ssf_slam_b200.model import set_upconv_pm
+    inter, sd = setup["inter"], setup["sd"]
+    want = tp.set_upconv(sd, name, 16, inter["pcs1"][lvl], inter["pcs1"][lvl + 1], inter["f1"][lvl], inter["f1"][lvl + 1])
+    got = set_upconv_pm(setup["W"][name], 16, _pm(inter["pcs1"][lvl]), _pm(inter["pcs1"][lvl + 1]), _pm(inter["f1"][lvl]),
+                        _pm(inter["f1"][lvl + 1]))
+    err = float((_cm(got) - want).abs().max())
+    assert err < 2e-5 * max(1.0, float(want.abs().max())), err
+
+
+def test_upsample_and_warp_teacher_forced(setup):
+    from ssf_slam_b200.model import point_warping_pm, upsample_pm
+    inter = setup["inter"]
+    cf, cb, ff, flow = inter["l3"]
+    for val, k in ((flow, 5), (ff, 5), (cf, 3)):
+        want = tp.upsample_flow(inter["pcs1"][2], inter["pcs1"][3], val, k=k)
+        got = upsample_pm(_pm(inter["pcs1"][2]), _pm(inter["pcs1"][3]), _pm(val), k)
+        assert float((_cm(got) - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+    coarse = tp.upsample_flow(inter["pcs1"][2], inter["pcs1"][3], flow, k=5)
+    want = tp.point_warping(inter["pcs1"][2], inter["pcs2"][2], coarse, 5)
+    got = point_warping_pm(_pm(inter["pcs1"][2]), _pm(inter["pcs2"][2]), _pm(coarse), 5)
+    assert float((_cm(got) - want).abs().max()) < 1e-5
+
+
+def test_cost_volume_level3_teacher_forced(setup):
+    """flow3_r: no flow / no sf_feat inputs.  Inputs come from the oracle so neighbour sets are identical."""
+    from ssf_slam_b200.model import cost_volume_pm
+    inter, sd = setup["inter"], setup["sd"]
+    u1 = tp.set_upconv(sd, "su3", 16, inter["pcs1"][3], inter["pcs1"][4], inter["f1"][3], inter["f1"][4])
+    u2 = tp.set_upconv(sd, "su3", 16, inter["pcs2"][3], inter["pcs2"][4], inter["f2"][3], inter["f2"][4])
+    want = tp.cost_volume(sd, "flow3_r.cost", 16, False, inter["pcs1"][3], inter["pcs2"][3], None, u1, u2)
+    got = cost_volume_pm(setup["W"]["flow3_r"], _pm(inter["pcs1"][3]), _pm(inter["pcs2"][3]), None, _pm(u1), None, _pm(u2), None)
+    names = ("cost_fwd", "cost_bwd", "feats", "flow")
+    for n, w_, g_ in zip(names, want, got):
+        w_ = w_ if n != "cost_bwd" else torch.nn.functional.pad(w_, (0, g_.shape[1] - w_.shape[2]))
+        err = float((_cm(g_) - w_).abs().max())
+        assert err < 3e-5 * max(1.0, float(w_.abs().max())), (n, err)
+
+
+def test_cost_volume_level2_teacher_forced(setup):
+    """flow2_r: warping, flow-shifted kNN, sf_feat and the 2-segment feature inputs."""
+    from ssf_slam_b200.model import cost_volume_pm, point_warping_pm
+    inter, sd = setup["inter"], setup["sd"]
+    p1, p2, p1s = inter["pcs1"][2], inter["pcs2"][2], inter["pcs1"][3]
+    u31 = tp.set_upconv(sd, "su3", 16, inter["pcs1"][3], inter["pcs1"][4], inter["f1"][3], inter["f1"][4])
+    u32 = tp.set_upconv(sd, "su3", 16, inter["pcs2"][3], inter["pcs2"][4], inter["f2"][3], inter["f2"][4])
+    u1 = tp.set_upconv(sd, "su2", 16, p1, p1s, inter["f1"][2], u31)
+    u2 = tp.set_upconv(sd, "su2", 16, p2, inter["pcs2"][3], inter["f2"][2], u32)
+    cf, cb, ff, flow = inter["l3"]
+    coarse = tp.upsample_flow(p1, p1s, flow, k=5)
+    sf_feat = tp.upsample_flow(p1, p1s, ff, k=5)
+    cfu = tp.leaky_conv1d(sd, "deconv3_2", tp.upsample_flow(p1, p1s, cf))
+    cbu = tp.leaky_conv1d(sd, "deconv3_2", tp.upsample_flow(p1, p1s, cb))
+    want = tp.refine_flow(sd, "flow2_r", 16, True, p1, p2, torch.cat([u1, cfu], 1), torch.cat([u2, cbu], 1), 5, coarse, sf_feat)
+    warped = point_warping_pm(_pm(p1), _pm(p2), _pm(coarse), 5)
+    got = cost_volume_pm(setup["W"]["flow2_r"], _pm(p1), _pm(p2), warped, _pm(u1), _pm(cfu), _pm(u2), _pm(cbu),
+                         sf=_pm(coarse), sf_feat=_pm(sf_feat))
+    for n, w_, g_ in zip(("cost_fwd", "cost_bwd", "feats", "flow"), want, got):
+        w_ = w_ if n != "cost_bwd" else torch.nn.functional.pad(w_, (0, g_.shape[1] - w_.shape[2]))
+        err = float((_cm(g_) - w_).abs().max())
+        assert err < 3e-5 * max(1.0, float(w_.abs().max())), (n, err)
+    for n, w_ in zip(("cost_fwd", "cost_bwd", "feats", "flow"), want):
+        assert float((inter["l2"][("cost_fwd", "cost_bwd", "feats", "flow").index(n)] - w_).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [2048, 8192])
+def test_tflow_end_to_end_vs_reference_golden(setup, golden_dir, n):
+    g = np.load(os.path.join(golden_dir, "tflow_n%d.npz" % n))
+    net = setup["net"]
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0).cuda()
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0).cuda()
+    flows, fps = net(pc1, pc2)
+    for i in range(3):
+        assert np.array_equal(fps[i][0].cpu().numpy(), g["fps%d" % (i + 1)]), "fps level %d" % (i + 1)
+    errs = [float(np.abs(flows[i][0].cpu().numpy() - g["flow%d" % i]).max()) for i in range(4)]
+    print("flow max-abs error per level (fine -> coarse):", errs)
+    assert flows[0].shape == (1, 3, n) and flows[1].shape == (1, 3, 2048)
+    for e in errs:
+        assert e <= FLOW_TOL, errs
+
+
+def test_batch_independence(setup, golden_dir):
+    """B=2 batch == two B=1 calls (the reference forward is batch-independent on CPU)."""
+    g = np.load(os.path.join(golden_dir, "tflow_n2048.npz"))
+    net = setup["net"]
+    a = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0).cuda()
+    b = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0).cuda()
+    f1, _ = net(a, b)
+    f2, _ = net(torch.cat([a, b]), torch.cat([b, a]))
+    assert torch.equal(f1[0][0], f2[0][0])
+    f3, _ = net(b, a)
+    assert torch.equal(f3[0][0], f2[0][1])
+
+
+def test_state_dict_with_dataparallel_prefix(setup):
+    from ssf_slam_b200.model import prepare_weights
+    sd = {"module." + k: v for k, v in setup["sd"].items()}
+    W = prepare_weights(sd, torch.device("cuda:0"))
+    assert torch.equal(W["pc0"], setup["W"]["pc0"])
+
+
+def test_frontend_pipeline_host_buffers(setup, golden_dir):
+    from oracle import frontend as ofe
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    g = np.load(os.path.join(golden_dir, "tflow_n2048.npz"))
+    fe = SceneFlowFrontEnd(setup["net"], tau=0.10)
+    out = fe.process(g["pos1"][None], g["pos2"][None], return_flow=True)
+    flow = out["flow"][0].numpy()
+    assert np.abs(flow.T - g["flow0"]).max() <= FLOW_TOL
+    want = ofe.masker_spec(g["pos1"], flow, 0.10)  # mask/pose spec on the very flow the GPU produced
+    assert np.array_equal(out["mask"][0].numpy(), want["mask"])
+    assert np.array_equal(out["odom"][0].numpy(), want["odom"])

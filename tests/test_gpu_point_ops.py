@@ -1,0 +1,142 @@
+"""GPU parity: point operators through the C ABI vs the CPU oracle (bit-exact indices, exact distances)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import point_ops as po  # noqa: E402  (checker only)
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def pu(oracle_c):
+    from ssf_slam_b200 import pointnet2_utils
+    return pointnet2_utils
+
+
+def _cloud(seed, B, N, dup=True, scale=30.0):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-scale, scale, (B, N, 3)).astype(np.float32)
+    if dup and N >= 64:
+        x[:, N // 2:N // 2 + N // 8] = x[:, :N // 8]  # exact duplicates -> exact ties
+    return x
+
+
+def test_golden_point_ops(pu, golden_dir):
+    g = np.load(os.path.join(golden_dir, "point_ops.npz"))
+    xyz, query = _cuda(g["xyz"]), _cuda(g["query"])
+    assert np.array_equal(pu.furthest_point_sample(xyz, 256).cpu().numpy(), g["fps256"])
+    for name, k in (("knn16", 16), ("knn7", 7)):
+        d, i = pu.knn(k, query, xyz)
+        assert np.array_equal(i.cpu().numpy(), g[name + "_idx"])
+        assert np.array_equal(d.cpu().numpy(), g[name + "_dist"])
+    d, i = pu.three_nn(query, xyz)
+    assert np.array_equal(i.cpu().numpy(), g["nn3_idx"]) and np.array_equal(d.cpu().numpy(), g["nn3_dist"])
+    for r in (0.5, 2.0, 4.0):
+        bi, bc = pu.ball_query(r, 16, xyz, query, return_count=True)
+        assert np.array_equal(bi.cpu().numpy(), g["ball_r%g_idx" % r])
+        assert np.array_equal(bc.cpu().numpy(), g["ball_r%g_cnt" % r])
+
+
+@pytest.mark.parametrize("N,npoint", [(8192, 2048), (2048, 512), (512, 256), (256, 128), (100, 37), (1, 1), (5000, 300),
+                                      (130, 140), (16384, 1024), (20000, 512), (65536, 2048)])
+def test_fps(pu, N, npoint):
+    B = 3 if N <= 8192 else 2
+    x = _cloud(N, B, N)
+    got = pu.furthest_point_sample(_cuda(x), npoint).cpu().numpy()
+    assert np.array_equal(got, po.c_fps(x, npoint))
+
+
+@pytest.mark.parametrize("Nq,Nr,k", [(2048, 8192, 16), (8192, 8192, 16), (8192, 2048, 7), (512, 256, 5), (128, 256, 8),
+                                     (8192, 2048, 3), (1000, 1501, 16), (77, 33, 32), (3, 1, 1), (4096, 5000, 16)])
+def test_knn(pu, Nq, Nr, k):
+    B = 2
+    ref = _cloud(Nq + Nr, B, Nr)
+    q = _cloud(7 * Nq + 1, B, Nq, dup=False)
+    q[:, : min(Nq, Nr) // 2] = ref[:, : min(Nq, Nr) // 2]  # queries coinciding with reference points (d = 0 ties)
+    d, i = pu.knn(k, _cuda(q), _cuda(ref))
+    od, oi = po.c_knn(k, q, ref)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    assert np.array_equal(d.cpu().numpy(), od)
+
+
+def test_knn_offset_matches_materialised_sum(pu):
+    ref = _cloud(1, 2, 4096)
+    q = _cloud(2, 2, 2048, dup=False)
+    off = (np.random.default_rng(3).standard_normal(q.shape) * 0.3).astype(np.float32)
+    _, i1 = pu.knn(16, _cuda(q), _cuda(ref), offset=_cuda(off))
+    _, oi = po.c_knn(16, q + off, ref)
+    assert np.array_equal(i1.cpu().numpy(), oi)
+
+
+def test_knn_all_ties(pu):
+    ref = np.zeros((1, 300, 3), np.float32)
+    d, i = pu.knn(16, _cuda(np.zeros((1, 5, 3), np.float32)), _cuda(ref))
+    assert np.array_equal(i.cpu().numpy()[0], np.tile(np.arange(16), (5, 1))) and float(d.abs().max()) == 0.0
+
+
+def test_knn_rejects_bad_k(pu):
+    from ssf_slam_b200._native import SsfError
+    with pytest.raises(SsfError):
+        pu.knn(9, torch.zeros(1, 4, 3).cuda(), torch.zeros(1, 4, 3).cuda())  # k > Nr
+    with pytest.raises(SsfError):
+        pu.knn(64, torch.zeros(1, 4, 3).cuda(), torch.zeros(1, 100, 3).cuda())
+
+
+@pytest.mark.parametrize("N,S,radius,nsample", [(8192, 2048, 0.5, 16), (8192, 2048, 4.0, 32), (1501, 333, 2.0, 16),
+                                                (65536, 2048, 1.0, 16), (100, 10, 0.001, 8)])
+def test_ball_query(pu, N, S, radius, nsample):
+    xyz = _cloud(N + S, 2, N, scale=20.0)
+    new = xyz[:, :: max(1, N // S)][:, :S].copy()
+    if radius < 0.01:
+        new = new + 7.0  # nobody in range
+    bi, bc = pu.ball_query(radius, nsample, _cuda(xyz), _cuda(new), return_count=True)
+    oi, oc = po.c_ball_query(radius, nsample, xyz, new)
+    assert np.array_equal(bc.cpu().numpy(), oc)
+    assert np.array_equal(bi.cpu().numpy(), oi)
+
+
+@pytest.mark.parametrize("C,N,M,S", [(3, 8192, 2048, 16), (96, 8192, 8192, 16), (64, 2048, 8192, 7), (5, 100, 33, 3), (1, 7, 1, 1)])
+def test_grouping_and_gather(pu, C, N, M, S):
+    rng = np.random.default_rng(C * N + M)
+    feat = rng.standard_normal((2, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, (2, M, S)).astype(np.int32)
+    got = pu.grouping_operation(_cuda(feat), _cuda(idx)).cpu().numpy()
+    assert np.array_equal(got, po.c_group(feat, idx))
+    g1 = pu.gather_operation(_cuda(feat), _cuda(idx[:, :, 0].copy())).cpu().numpy()
+    assert np.array_equal(g1, po.gather_operation(torch.from_numpy(feat), torch.from_numpy(idx[:, :, 0].copy())).numpy())
+
+
+def test_three_interpolate(pu):
+    rng = np.random.default_rng(9)
+    feat = rng.standard_normal((2, 33, 500)).astype(np.float32)
+    idx = rng.integers(0, 500, (2, 1000, 3)).astype(np.int32)
+    w = rng.random((2, 1000, 3)).astype(np.float32)
+    got = pu.three_interpolate(_cuda(feat), _cuda(idx), _cuda(w)).cpu().numpy()
+    want = po.three_interpolate(torch.from_numpy(feat), torch.from_numpy(idx), torch.from_numpy(w)).numpy()
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("L,C,n", [(4096 * 16, 1, 4096), (2048 * 16, 64, 2048), (1000, 5, 37), (50, 3, 200)])
+def test_scatter(L, C, n):
+    from ssf_slam_b200 import scatter
+    rng = np.random.default_rng(L + C)
+    src = rng.standard_normal((2, L, C)).astype(np.float32)
+    index = rng.integers(0, n, (2, L)).astype(np.int64)
+    index[:, 0] = n - 1
+    sm = scatter.scatter_softmax(_cuda(src), _cuda(index), dim=1).cpu()
+    ss = scatter.scatter_sum(_cuda(src), _cuda(index), dim=1).cpu()
+    osm = po.scatter_softmax(torch.from_numpy(src), torch.from_numpy(index), dim=1)
+    oss = po.scatter_sum(torch.from_numpy(src), torch.from_numpy(index), dim=1)
+    assert ss.shape == oss.shape
+    assert float((sm - osm).abs().max()) <= 2e-6   # fp32 exp/ordering tolerance
+    assert float((ss - oss).abs().max()) <= 1e-4 * max(1.0, float(oss.abs().max()))
+    # run-to-run determinism (no atomics in the accumulation)
+    ss2 = scatter.scatter_sum(_cuda(src), _cuda(index), dim=1).cpu()
+    assert torch.equal(ss, ss2)

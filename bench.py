@@ -261,13 +261,19 @@ def main():
     roof = None
     if top is not None:
         t = shares[top]
-        # the cost-volume core dominates; its level-0 launch (N1 = N, m = 64) is the single largest kernel
+        import re
+        dims = dict((k, int(v)) for k, v in re.findall(r"(\w+)=(\d+)", top))
+        avg_s = t["ms"] / t["calls"] * 1e-3
         if top.startswith("cost_volume"):
-            flops = B * sum(cost_volume_flops(n1, m) for n1, m in ((N, 64), (2048, 64), (512, 128), (256, 256))) / 4.0
-            ach = flops / (t["ms"] / t["calls"] * 1e-3) / 1e12
+            ach = B * cost_volume_flops(dims["N1"], dims["m"]) / avg_s / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
                     "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["source"],
-                    "note": "fp32 FFMA realisation (fp32 parity path); algorithmic 2*MAC averaged over the 4 pyramid levels' launches"}
+                    "note": "fp32 FFMA realisation (fp32-parity path); algorithmic 2*MAC of one launch over B clouds / its mean duration"}
+        elif top.startswith("knn"):
+            byts = B * (12.0 * (dims["Nq"] + dims["Nr"]) + 4.0 * dims["Nq"] * dims["k"])
+            roof = {"kernel": top, "bound": "hbm", "achieved": byts / avg_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": byts / avg_s / 1e9 / pk["hbm"], "traffic": None, "peak_source": pk["source"],
+                    "note": "brute-force kNN is FP32-ALU bound (Nq*Nr pair evaluations), not HBM bound; bytes are compulsory traffic"}
         else:
             roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
                     "traffic": None, "peak_source": pk["source"]}

@@ -187,7 +187,11 @@ def cost_volume(sd, prefix, nsample, use_flow, xyz1, xyz2, xyz2w, points1, point
     key = idxw.view(B, -1).long()
     cw_flat = cw.permute(0, 3, 2, 1).reshape(B, -1, c.shape[1])
     w_bwd = ops.scatter_softmax(gw.permute(0, 3, 2, 1).reshape(B, -1, gw.shape[1]), key, dim=1)
-    cost_bwd = ops.scatter_sum(cw_flat * w_bwd, key, dim=1)
+    # torch_scatter sizes the output as key.max()+1 (soflow.py:481); the reference then gathers it with knn_idx
+    # (:489) and upsamples it with indices up to N2-1, a latent out-of-bounds read whenever the highest-index pc2
+    # point is nobody's neighbour.  The oracle allocates all N2 rows (zeros for
+    # unreferenced points): identical wherever the reference is defined.
+    cost_bwd = ops.scatter_sum(cw_flat * w_bwd, key, dim=1, dim_size=xyz2.shape[2])
     cost_fwd = torch.sum(w_fwd * c, dim=2)
 
     g_bwd = _gather_rows(cost_bwd, idx)

@@ -278,15 +278,18 @@ interpolate_kernel(const float* __restrict__ query, const float* __restrict__ sr
     float norm = 0.f;
     for (int j = 0; j < k; ++j) norm += __shfl_sync(0xffffffffu, inv, j);  // slot order, as torch.sum over the last dim
     const float w = inv / norm;
-    for (int c = lane; c < C; c += 32) {
+    for (int c0 = 0; c0 < C; c0 += 32) {  // warp-uniform trip count: every lane takes part in the shuffles
+        const int c = c0 + lane;
         float v = 0.f;
         for (int j = 0; j < k; ++j) {
             const float wj = __shfl_sync(0xffffffffu, w, j);
             const int ij = __shfl_sync(0xffffffffu, id, j);
-            v += wj * __ldg(src_val + ((size_t)b * M + ij) * C + c);
+            if (c < C) v += wj * __ldg(src_val + ((size_t)b * M + ij) * C + c);
         }
-        if (mode == 1) v = (c == 0 ? qx : (c == 1 ? qy : qz)) - v;
-        out[((size_t)b * N + n) * C + c] = fminf(fmaxf(v, -clampv), clampv);
+        if (c < C) {
+            if (mode == 1) v = (c == 0 ? qx : (c == 1 ? qy : qz)) - v;
+            out[((size_t)b * N + n) * C + c] = fminf(fmaxf(v, -clampv), clampv);
+        }
     }
 }
 

@@ -1,0 +1,92 @@
+"""CPU: host-side logic -- state_dict surface, BN folding, wire formats, sharding (gloo, world size 2), generator."""
+import os
+import struct
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_surface_matches_reference_format():
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200.weights import random_init_state_dict
+    sd = random_init_state_dict(0)           # keys/shapes verified by a strict load into the unmodified reference (gen_golden)
+    net = TFlow(npoint=8192)
+    assert len(net.state_dict()) == 317 and sum(p.numel() for p in net.parameters()) == 2259344
+    net.load_state_dict(sd, strict=True)
+    assert set(net.state_dict()) == set(sd)
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+
+
+def test_bn_folding_equals_conv_bn_eval():
+    from ssf_slam_b200.model import prepare_weights
+    from ssf_slam_b200.weights import random_init_state_dict
+    sd = random_init_state_dict(3)
+    W = prepare_weights(sd, "cpu")
+    x = torch.randn(2, 35, 7, 5)
+    ref = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, sd["sa1.mlp_convs.0.weight"]),
+                                         sd["sa1.mlp_bns.0.running_mean"], sd["sa1.mlp_bns.0.running_var"],
+                                         sd["sa1.mlp_bns.0.weight"], sd["sa1.mlp_bns.0.bias"], False, 0.1, 1e-5)
+    xt = x.permute(0, 2, 3, 1)  # rows x channels; input order cat[dxyz(3) | feats(32)]
+    got = xt[..., :3] @ W["sa1"]["Wd"] + xt[..., 3:] @ W["sa1"]["Wg"] + W["sa1"]["b1"]
+    assert torch.allclose(got.permute(0, 3, 1, 2), ref, atol=1e-5)
+    f = W["flow0_r"]
+    assert f["Wab"].shape == (192, 128) and f["W3"].shape == (131, 64) and f["W4"].shape == (195, 64) and f["wn3"].shape == (32,)
+
+
+def test_wire_formats():
+    from ssf_slam_b200 import wire
+    pts = np.arange(12, dtype=np.float64).reshape(4, 3)
+    d = wire.pointcloud2_dict(pts)
+    assert d["point_step"] == 12 and d["row_step"] == 48 and d["width"] == 4 and d["height"] == 1 and not d["is_dense"]
+    assert d["data"] == pts.astype(np.float32).tobytes() and [f[:2] for f in d["fields"]] == [("x", 0), ("y", 4), ("z", 8)]
+    assert len(wire.pointcloud2_dict(pts, declare_intensity=True)["fields"]) == 4
+    o = [1.0, 2, 3, 0, 0, 0, 1]
+    assert struct.unpack("<7d", wire.odom_payload(o)) == tuple(o)
+    ser = wire.serialize_float64_multiarray(o)
+    assert len(ser) == 12 + 56 and struct.unpack("<III", ser[:12]) == (0, 0, 7)
+    lines = wire.integrate_odometry([[1, 0, 0, 0, 0, np.sin(np.pi / 4), np.cos(np.pi / 4)], [1, 0, 0, 0, 0, 0, 1]])
+    last = [float(v) for v in lines[-1].split()]
+    assert np.allclose(last[1:4], [1, 1, 0], atol=1e-9)  # second step moves along the rotated x axis
+
+
+def test_synthetic_generator_shapes_and_determinism():
+    from ssf_slam_b200 import synth
+    a, b = synth.make_pair(0, 1024), synth.make_pair(0, 1024)
+    for k in ("pos1", "pos2", "gt", "ego_flow", "s_fg_mask", "t_fg_mask", "sem", "inst"):
+        assert np.array_equal(a[k], b[k])
+    assert a["pos1"].shape == (1024, 3) and a["pos1"].dtype == np.float32 and set(np.unique(a["s_fg_mask"])) <= {0, 1}
+    assert np.abs(a["gt"] - a["ego_flow"])[a["s_fg_mask"] == 0].max() == 0.0
+    assert synth.dense_cloud(5000, 4096).shape == (4096, 3)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from ssf_slam_b200.shard import gather_results, my_sequences
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seqs = my_sequences(64, rank, world)
+    odom = torch.full((2, 3, 7), float(rank), dtype=torch.float64)
+    mask = torch.full((2, 3, 16), rank, dtype=torch.uint8)
+    od, mk = gather_results(odom, mask)
+    q.put((rank, seqs, od[:, 0, 0, 0].tolist(), mk[:, 0, 0, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_final_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert res[0][1] == list(range(0, 64, 2)) and res[1][1] == list(range(1, 64, 2))
+    for r in res:
+        assert r[2] == [0.0, 1.0] and r[3] == [0, 1]

@@ -124,6 +124,12 @@ int ssf_frontend(const float* points, const float* flow, int B, int N, int mode,
                  const int* sem, unsigned long long movable_bits, const int* inst, int n_inst, float tau,
                  unsigned char* mask_out, double* odom_out, double* pose_out, void* stream);
 
+/* ---- tensor-core bring-up / regression: Y[128,N] = X[128,K].W[N,K]^T on tcgen05 kind::tf32 (3xTF32 when passes == 3);
+ * Whi_img / Wlo_img are the split weights in the no-swizzle K-major UMMA image (ssf_slam_b200.tc.weight_image);
+ * mode 0: A operand from TMEM, mode 1: A operand from shared memory */
+int ssf_tc_gemm_test(const float* X, const float* Whi_img, const float* Wlo_img, int K, int N, int mode, int passes,
+                     float* Y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

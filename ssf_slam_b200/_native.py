@@ -42,6 +42,7 @@ SIGNATURES = {
     "ssf_group_mlp_max": ("ppppppp" + "ppi" + "ppi" + "iiiiii" + "pp", _I),
     "ssf_cost_volume": ("p" * 16 + "f" + "pppp" + "iiii" + "pppp" + "p", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
+    "ssf_tc_gemm_test": ("pppiiiipp", _I),
 }
 
 _lib = None

@@ -1,0 +1,107 @@
+// tcgen05 / TMEM helpers (inline PTX, sm_100a) shared by the tensor-core kernels.
+//
+// Contraction scheme: fp32-faithful "3xTF32".  Every fp32 operand x is split into hi = rna_tf32(x) and
+// lo = x - hi (exact); D += Alo.Whi + Ahi.Wlo + Ahi.Whi on `tcgen05.mma.kind::tf32` with fp32 accumulation in
+// TMEM.  The dropped Alo.Wlo term is <= 2^-22 relative, i.e. below fp32 rounding of the sum.
+//
+// Operand layouts:
+//  * B (weights, N x K, K-major) lives in shared memory in the canonical no-swizzle ("interleave") UMMA layout:
+//    8-row x 16-byte core matrices; byte(n, k) = (k/4)*LBO + (n/8)*SBO + (n%8)*16 + (k%4)*4 with SBO = 128,
+//    LBO = (N/8)*128.  The host pre-arranges this image (hi and lo) once per layer, so a plain bulk copy
+//    (cp.async.bulk, no tensor map) brings it in.
+//  * A (activations, 128 x K) is read from TMEM (`[taddr]` form): row m = TMEM lane m, element k = column a_col + k.
+//  * D (128 x N fp32) in TMEM: row m = lane m, column d_col + n.
+#pragma once
+#include "ssf_common.cuh"
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one full warp allocates `cols` (power of two >= 32) TMEM columns; base address is written to *slot (shared memory)
+__device__ __forceinline__ void tc_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssf_smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// instruction descriptor for kind::tf32: D fp32, A/B tf32, both K-major, dense
+__host__ __device__ constexpr uint32_t tc_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T      (single thread issues)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
+}
+
+// TMEM <-> registers, 32 lanes x 32 bit x 8 columns: thread (lane i of warp w) <-> TMEM lane 32*(w%4)+i, columns col..col+7
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// hi = round-to-nearest tf32 (10-bit mantissa), lo = x - hi (exact in fp32)
+__device__ __forceinline__ void tc_split(float x, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+// TMEM address of (lane base of this warp, column)
+__device__ __forceinline__ uint32_t tc_addr(uint32_t tmem_base, int warp, int col) {
+    return tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
+}
+
+// byte offset of element (row n, k) in the no-swizzle K-major image of an R-row operand
+__host__ __device__ constexpr uint32_t tc_img_off(int n, int k, int R) {
+    return (uint32_t)((k >> 2) * ((R >> 3) * 128) + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4);
+}

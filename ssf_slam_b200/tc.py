@@ -1,0 +1,24 @@
+"""Host-side preparation for the tcgen05 (tensor-core) kernels: fp32 -> (hi, lo) TF32 split and the shared-memory
+operand image the UMMA descriptors expect (see csrc/tc_common.cuh)."""
+import torch
+
+
+def split_tf32(w):
+    """hi = round-to-nearest(ties away) to 10 mantissa bits (== cvt.rna.tf32.f32), lo = w - hi (exact in fp32)."""
+    bits = w.contiguous().view(torch.int32)
+    hi = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, w - hi
+
+
+def kmajor_image(w):
+    """w [R, K] (row r, K contiguous) -> flat fp32 tensor in the no-swizzle K-major core-matrix order:
+    byte(r, k) = (k/4)*(R/8)*128 + (r/8)*128 + (r%8)*16 + (k%4)*4."""
+    R, K = w.shape
+    assert R % 8 == 0 and K % 4 == 0
+    return w.view(R // 8, 8, K // 4, 4).permute(2, 0, 1, 3).contiguous().view(-1)
+
+
+def weight_image(w):
+    """w [N, K] (the reference's [Cout, Cin] conv weight) -> (hi image, lo image)."""
+    hi, lo = split_tf32(w.float())
+    return kmajor_image(hi), kmajor_image(lo)

@@ -15,8 +15,8 @@ def _run(K, N, mode, passes, seed=0):
     W = torch.randn(N, K, generator=g)
     hi, lo = tc.weight_image(W)
     Y = torch.full((128, N), float("nan"), device="cuda")
-    nat.check(nat.lib().ssf_tc_gemm_test(nat.ptr(X.cuda()), nat.ptr(hi.cuda()), nat.ptr(lo.cuda()), K, N, mode, passes,
-                                         nat.ptr(Y), nat.stream()))
+    Xd, hid, lod = X.cuda(), hi.cuda(), lo.cuda()  # keep the device tensors alive across the launch
+    nat.check(nat.lib().ssf_tc_gemm_test(nat.ptr(Xd), nat.ptr(hid), nat.ptr(lod), K, N, mode, passes, nat.ptr(Y), nat.stream()))
     torch.cuda.synchronize()
     ref = (X.double() @ W.double().t())
     err = float((Y.cpu().double() - ref).abs().max())

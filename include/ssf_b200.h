@@ -112,6 +112,15 @@ int ssf_cost_volume(const float* Gab, const float* Hab, const float* W2a, const 
                     const float* wn3, float bn3, const float* xyz1, const float* xyz2, const int* idx, const int* idxw,
                     int B, int N1, int N2, int m, float* cost_fwd, float* cost_fwd_cm, float* gw, float* Cw, void* stream);
 
+/* tcgen05 / TMEM realisation of the same core for m == 64 (levels 0 and 1): 3xTF32 split GEMMs with fp32 TMEM
+ * accumulators, persistent CTA per SM.  wblob / params come from ssf_slam_b200.tc.cost_volume_tc_pack
+ * (ssf_cost_volume_tc_blob_bytes() bytes, ssf_cost_volume_tc_param_floats() floats); n_sm <= 0 -> 148. */
+long long ssf_cost_volume_tc_blob_bytes(void);
+int ssf_cost_volume_tc_param_floats(void);
+int ssf_cost_volume_tc(const float* Gab, const float* Hab, const float* H3, const void* wblob, const float* params,
+                       const float* xyz1, const float* xyz2, const int* idx, const int* idxw, int B, int N1, int N2,
+                       int m, float* cost_fwd, float* cost_fwd_cm, float* gw, float* Cw, int n_sm, void* stream);
+
 /* ---- B-frontend: dynamic mask + static-point ego-motion (ASF/main_sju_occ_ros.py:257-284,455-473;
  * scripts/PointCloudOdometry.py:15-33,91-101) ----
  * mode 0: weighted Kabsch on the points whose in_mask is 0 (GT / dataset mask variants);

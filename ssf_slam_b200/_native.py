@@ -41,6 +41,9 @@ SIGNATURES = {
     "ssf_interpolate": ("ppppiiiiiifpp", _I),
     "ssf_group_mlp_max": ("ppppppp" + "ppi" + "ppi" + "iiiiii" + "pp", _I),
     "ssf_cost_volume": ("p" * 16 + "f" + "pppp" + "iiii" + "pppp" + "p", _I),
+    "ssf_cost_volume_tc": ("p" * 9 + "iiii" + "pppp" + "ip", _I),
+    "ssf_cost_volume_tc_blob_bytes": ("", _I64),
+    "ssf_cost_volume_tc_param_floats": ("", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
     "ssf_tc_gemm_test": ("pppiiiipp", _I),
 }

@@ -9,6 +9,9 @@ import torch
 from . import _native as nat
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+# tcgen05 realisation of the dense layers where one exists (False: SIMT fp32 kernels everywhere; used by the tests
+# that compare the two realisations)
+USE_TC = True
 
 
 def _rows(x):
@@ -101,6 +104,10 @@ def cost_volume(Gab, Hab, w, H3, xyz1, xyz2, idx, idxw, m):
     gw = torch.empty(B, N1 * 16, dtype=torch.float32, device=dev)
     Cw = torch.empty(B, N1 * 16, m, dtype=torch.float32, device=dev)
     p = nat.ptr
+    if USE_TC and "tc_blob" in w:
+        nat.check(nat.lib().ssf_cost_volume_tc(p(Gab), p(Hab), p(H3), p(w["tc_blob"]), p(w["tc_par"]), p(xyz1), p(xyz2), p(idx),
+                                               p(idxw), B, N1, N2, m, p(cost_fwd), p(cost_fwd_cm), p(gw), p(Cw), 0, nat.stream()))
+        return cost_fwd, cost_fwd_cm, gw, Cw
     nat.check(nat.lib().ssf_cost_volume(p(Gab), p(Hab), p(w["W2a"]), p(w["b2a"]), p(w["W2w"]), p(w["b2w"]), p(w["W3a"]),
                                         p(H3), p(w["W3d"]), p(w["W3b"]), p(w["b3b"]), p(w["Wn1"]), p(w["bn1"]), p(w["Wn2"]),
                                         p(w["bn2"]), p(w["wn3"]), float(w["bn3"]), p(xyz1), p(xyz2), p(idx), p(idxw), B, N1,

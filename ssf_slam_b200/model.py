@@ -21,6 +21,7 @@ import torch.nn as nn
 
 from . import functional as F_
 from . import _native as nat
+from . import tc
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = F_.ACT_NONE, F_.ACT_RELU, F_.ACT_LEAKY
 
@@ -196,6 +197,13 @@ def prepare_weights(state_dict, device):
                  W4=dev(_kmajor(w4)), b4=dev(b4),                              # rows [0,m) fwd | [m,2m) bwd | [2m,2m+F) sf_feat | dir
                  W42=dev(_kmajor(w2(p + ".mlp_convs4.1.weight"))), b42=dev(sd[p + ".mlp_convs4.1.bias"].float()),
                  fc=dev(_kmajor(w2(p + ".fc.weight"))), fcb=dev(sd[p + ".fc.bias"].float()))
+        if m == 64:  # tensor-core path (csrc/cost_volume_tc.cu): split TF32 weight images
+            blob, par = tc.cost_volume_tc_pack(
+                w2(p + ".mlp_convs.1.weight"), w2(p + ".mlp_convs2.1.weight"), w3[:, :m], w2(p + ".mlp_convs3.1.weight"),
+                wn1, wn2, sd[p + ".mlp_convs.1.bias"].float(), sd[p + ".mlp_convs2.1.bias"].float(),
+                sd[p + ".mlp_convs3.1.bias"].float(), bn1, bn2, w2(p + ".weightnet1.6.weight").reshape(-1),
+                _kmajor(w3)[m + Fc:], float(sd[p + ".weightnet1.6.bias"].reshape(-1)[0]))
+            d["tc_blob"], d["tc_par"] = dev(blob), dev(par)
         d["W3a"] = d["W3"][:m]
         d["W3d"] = d["W3"][m + Fc:]
         d["W4d"] = d["W4"][2 * m + Fc:]

@@ -22,3 +22,18 @@ def weight_image(w):
     """w [N, K] (the reference's [Cout, Cin] conv weight) -> (hi image, lo image)."""
     hi, lo = split_tf32(w.float())
     return kmajor_image(hi), kmajor_image(lo)
+
+
+def cost_volume_tc_pack(w2a, w2w, w3a, w3b, wn1, wn2, b2a, b2w, b3b, bn1, bn2, wn3, w3d, bn3):
+    """Weight blob + parameter block of ``ssf_cost_volume_tc`` (csrc/cost_volume_tc.cu) for m = 64.
+    Matrices are in the reference's [Cout, Cin] orientation (BatchNorm already folded); ``w3d`` is [3, m] K-major.
+    Blob = six chunks [hi image | lo image]: mlp_convs[1], mlp_convs2[1], mlp_convs3[0][:, :m], mlp_convs3[1],
+    weightnet1[0], weightnet1[3]; params = b2a b2w b3b bn1 bn2 wn3 W3d bn3 (fp32)."""
+    chunks = []
+    for w in (w2a, w2w, w3a, w3b, wn1, wn2):
+        hi, lo = weight_image(w.contiguous())
+        chunks += [hi, lo]
+    blob = torch.cat(chunks).contiguous()
+    params = torch.cat([b2a, b2w, b3b, bn1, bn2, wn3.reshape(-1), w3d.reshape(-1), torch.tensor([bn3, 0.0, 0.0, 0.0])]).float()
+    assert blob.numel() * 4 == 5 * 32768 + 16384 and params.numel() == 516
+    return blob, params.contiguous()

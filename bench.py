@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frame pairs in the cpu_baseline sample")
+    ap.add_argument("--shares-out", default=None, help="write the full per-kernel CUDA-event table (JSON) to this path")
     return ap.parse_args()
 
 
@@ -255,6 +256,10 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.shares_out:
+        with open(args.shares_out, "w") as f:
+            json.dump({k: {"ms_per_step": v["ms"] / min(K, 3), "calls_per_step": v["calls"] / min(K, 3), "share": v["share"]}
+                       for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])}, f, indent=1)
 
     pk = peaks()
     top = max(shares.items(), key=lambda kv: kv[1]["ms"])[0] if shares else None

@@ -121,6 +121,15 @@ int ssf_cost_volume_tc(const float* Gab, const float* Hab, const float* H3, cons
                        const float* xyz1, const float* xyz2, const int* idx, const int* idxw, int B, int N1, int N2,
                        int m, float* cost_fwd, float* cost_fwd_cm, float* gw, float* Cw, int n_sm, void* stream);
 
+/* CUDA-core pieces of the un-fused wide (m >= 128) cost volume; the dense layers between them are ssf_dense_tc calls.
+ * attention_mix: A, Aw [P,16,m] -> A + Q.Aw, Aw + Q^T.A, Q = softmax(-2) * softmax(-1) of <A_i,Aw_j> (soflow.py:420-422,453-458)
+ * softmax_pool : cost_fwd = sum_s softmax_s(g) * C  -> point-major [B,N1,m] and channel-major [B,m,N1] (soflow.py:469,486) */
+int ssf_attention_mix(const float* A, const float* Aw, long long n_points, int m, float* Amix, float* Awmix, void* stream);
+int ssf_softmax_pool(const float* g, const float* C, int B, int N1, int m, float* out_pm, float* out_cm, void* stream);
+
+/* tensor-core dense layer (argument block and documentation in ssf_dense.h) */
+#include "ssf_dense.h"
+
 /* ---- B-frontend: dynamic mask + static-point ego-motion (ASF/main_sju_occ_ros.py:257-284,455-473;
  * scripts/PointCloudOdometry.py:15-33,91-101) ----
  * mode 0: weighted Kabsch on the points whose in_mask is 0 (GT / dataset mask variants);

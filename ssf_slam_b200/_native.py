@@ -44,9 +44,27 @@ SIGNATURES = {
     "ssf_cost_volume_tc": ("p" * 9 + "iiii" + "pppp" + "ip", _I),
     "ssf_cost_volume_tc_blob_bytes": ("", _I64),
     "ssf_cost_volume_tc_param_floats": ("", _I),
+    "ssf_attention_mix": ("ppqippp", _I),
+    "ssf_softmax_pool": ("ppiiippp", _I),
+    "ssf_dense_tc": ("pp", _I),
+    "ssf_dense_args_bytes": ("", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
     "ssf_tc_gemm_test": ("pppiiiipp", _I),
 }
+
+
+
+class DenseArgs(ctypes.Structure):
+    """Mirror of ``ssf_dense_args`` (include/ssf_dense.h), field for field."""
+    _fields_ = [("a_mode", _I), ("K", _I), ("rows", _I64),
+                ("x1", _P), ("c1", _I), ("ld1", _I), ("x2", _P), ("c2", _I), ("ld2", _I),
+                ("G", _P), ("ldG", _I), ("offG", _I), ("H", _P), ("ldH", _I), ("offH", _I),
+                ("b1", _P), ("Wd1", _P), ("act1", _I),
+                ("idx", _P), ("S", _I), ("Nq", _I), ("Nsrc", _I), ("pos_src", _P), ("pos_q", _P),
+                ("wimg", _P), ("N", _I),
+                ("bias", _P), ("Hq", _P), ("ldHq", _I), ("Wd2", _P), ("act", _I), ("epi_mode", _I),
+                ("wvec", _P), ("b0", _F), ("y", _P), ("ldy", _I)]
+
 
 _lib = None
 

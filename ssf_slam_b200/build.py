@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libssf_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-I", os.path.join(os.path.dirname(HERE), "include")]
 
 
 def sources():
@@ -19,7 +19,7 @@ def sources():
 
 
 def headers():
-    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")))
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
 
 
 def _obj(src):

@@ -4,6 +4,8 @@ Tensors are torch CUDA fp32 ``[B, N, C]`` (features) / ``[B, N, 3]`` (coordinate
 weights are K-major ``[Cin, Cout]`` (see ``ssf_slam_b200.model.prepare_weights``).  Every function is one kernel
 launch of ours on the current stream; nothing here computes with torch ops.
 """
+import ctypes
+
 import torch
 
 from . import _native as nat
@@ -35,6 +37,77 @@ def linear(x1, Wt, cout, w_off1=0, x2=None, w_off2=0, bias=None, act=ACT_NONE, c
                                    nat.ptr(bias), rows, cout, act, float(clamp1), nat.ptr(add), cout, float(clamp2),
                                    nat.ptr(y), cout, nat.stream()))
     return y
+
+
+EPI_STORE, EPI_MAX, EPI_DOT = 0, 1, 2
+
+
+def dense_tc(wimg, N, K, *, x1=None, x2=None, G=None, offG=0, H=None, offH=0, b1=None, Wd1=None, act1=ACT_NONE, idx=None,
+             pos_src=None, pos_q=None, bias=None, Hq=None, Wd2=None, act=ACT_NONE, epi=EPI_STORE, wvec=None, b0=0.0, S=0):
+    """Tensor-core dense layer (csrc/dense_tc.cu, include/ssf_dense.h).  Rows: plain ``x1 | x2`` ([..., c]) or the grouped
+    first layer on the fly (``G`` [B,Nsrc,ldG], ``idx`` [B,Nq,S], optional per-point ``H`` [B,Nq,ldH]).  Returns
+    STORE: [rows..., N]; MAX: [B, Nq, N]; DOT: [rows...]."""
+    a = nat.DenseArgs()
+    p = nat.ptr
+    a.K, a.N, a.wimg = K, N, p(wimg)
+    a.S = S                      # plain rows pooled in groups of S (MAX epilogue without a gather)
+    if idx is not None:
+        B, Nq, S = idx.shape
+        a.idx, a.S, a.Nq = p(idx), S, Nq
+        a.pos_src, a.pos_q = p(pos_src), p(pos_q)
+    if G is not None:
+        a.a_mode = 1
+        a.G, a.ldG, a.offG, a.Nsrc = p(G), G.shape[-1], offG, G.shape[1]
+        if H is not None:
+            a.H, a.ldH, a.offH = p(H), H.shape[-1], offH
+        a.b1, a.Wd1, a.act1 = p(b1), p(Wd1), act1
+        rows, lead = B * Nq * S, (B, Nq, S)
+    else:
+        a.a_mode = 0
+        rows, c1, ld1 = _rows(x1)
+        a.x1, a.c1, a.ld1 = p(x1), c1, ld1
+        if x2 is not None:
+            r2, c2, ld2 = _rows(x2)
+            assert r2 == rows
+            a.x2, a.c2, a.ld2 = p(x2), c2, ld2
+        lead = tuple(x1.shape[:-1])
+        if pos_src is not None:
+            a.Nsrc = pos_src.shape[1]
+    a.rows = rows
+    a.bias, a.Wd2, a.act, a.epi_mode = p(bias), p(Wd2), act, epi
+    if Hq is not None:
+        a.Hq, a.ldHq = p(Hq), Hq.shape[-1]
+    dev = (x1 if x1 is not None else G).device
+    if epi == EPI_STORE:
+        y = torch.empty(lead + (N,), dtype=torch.float32, device=dev)
+        a.ldy = N
+    elif epi == EPI_MAX:
+        y = torch.empty((rows // S, N) if idx is None else (idx.shape[0], idx.shape[1], N), dtype=torch.float32, device=dev)
+        a.ldy = N
+    else:
+        y = torch.empty(lead, dtype=torch.float32, device=dev)
+        a.wvec, a.b0 = p(wvec), float(b0)
+    a.y = p(y)
+    nat.check(nat.lib().ssf_dense_tc(ctypes.byref(a), nat.stream()))
+    return y
+
+
+def attention_mix(A, Aw):
+    """A, Aw [..., 16, m] -> (A + Q.Aw, Aw + Q^T.A)  (ASF/utils/soflow.py:420-422,453-458)."""
+    m = A.shape[-1]
+    n_points = A.numel() // (16 * m)
+    Amix, Awmix = torch.empty_like(A), torch.empty_like(Aw)
+    nat.check(nat.lib().ssf_attention_mix(nat.ptr(A), nat.ptr(Aw), n_points, m, nat.ptr(Amix), nat.ptr(Awmix), nat.stream()))
+    return Amix, Awmix
+
+
+def softmax_pool(g, C):
+    """g [B,N1,16], C [B,N1,16,m] -> (cost_fwd [B,N1,m], channel-major copy [B,m,N1])  (ASF/utils/soflow.py:469,486)."""
+    B, N1, _, m = C.shape
+    out_pm = torch.empty(B, N1, m, dtype=torch.float32, device=C.device)
+    out_cm = torch.empty(B, m, N1, dtype=torch.float32, device=C.device)
+    nat.check(nat.lib().ssf_softmax_pool(nat.ptr(g), nat.ptr(C), B, N1, m, nat.ptr(out_pm), nat.ptr(out_cm), nat.stream()))
+    return out_pm, out_cm
 
 
 def gather_rows(src, idx):

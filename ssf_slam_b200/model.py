@@ -138,10 +138,16 @@ def prepare_weights(state_dict, device):
     def dev(t):
         return t.contiguous().to(device)
 
+    def img(w_nk):
+        """[Cout, Cin] -> tensor-core weight image (ssf_dense_tc)"""
+        return dev(tc.dense_image(w_nk.contiguous()))
+
     W["pc0"] = dev(_kmajor(w2("point_conv.0.composed_module.0.weight")))
     W["pc1"] = dev(_kmajor(w2("point_conv.1.composed_module.0.weight")))
+    W["pc1_img"] = img(w2("point_conv.1.composed_module.0.weight"))
     for name in ("deconv3_2", "deconv2_1", "deconv1_0"):
         W[name] = dev(_kmajor(w2(name + ".composed_module.0.weight")))
+        W[name + "_img"] = img(w2(name + ".composed_module.0.weight"))
 
     for name in ("sa1", "sa2", "sa3", "sa4"):
         layers = []
@@ -154,7 +160,8 @@ def prepare_weights(state_dict, device):
         w1, b1 = layers[0]
         W[name] = dict(Wd=dev(_kmajor(w1[:, :3])), Wg=dev(_kmajor(w1[:, 3:])), b1=dev(b1),
                        W2=dev(_kmajor(layers[1][0])), b2=dev(layers[1][1]), C2=layers[1][0].shape[0],
-                       W3=dev(_kmajor(layers[2][0])), b3=dev(layers[2][1]), C3=layers[2][0].shape[0], C1=w1.shape[0])
+                       W3=dev(_kmajor(layers[2][0])), b3=dev(layers[2][1]), C3=layers[2][0].shape[0], C1=w1.shape[0],
+                       Wg_img=img(w1[:, 3:]), W2_img=img(layers[1][0]), W3_img=img(layers[2][0]))
 
     for name in ("su3", "su2", "su1", "su0"):
         m1 = []
@@ -173,7 +180,8 @@ def prepare_weights(state_dict, device):
         W[name] = dict(Wg=dev(_kmajor(w1[:, :c2])), Wd=dev(_kmajor(w1[:, c2:])), b1=dev(b1), C1=w1.shape[0],
                        W2=dev(_kmajor(m1[1][0])), b2=dev(m1[1][1]), C2=m1[1][0].shape[0],
                        M1=dev(_kmajor(m2[0][0])), mb1=dev(m2[0][1]), MC1=m2[0][0].shape[0],
-                       M2=dev(_kmajor(m2[1][0])), mb2=dev(m2[1][1]), MC2=m2[1][0].shape[0])
+                       M2=dev(_kmajor(m2[1][0])), mb2=dev(m2[1][1]), MC2=m2[1][0].shape[0],
+                       Wg_img=img(w1[:, :c2]), W2_img=img(m1[1][0]), M1_img=img(m2[0][0]), M2_img=img(m2[1][0]))
 
     for name in ("flow3_r", "flow2_r", "flow1_r", "flow0_r"):
         p = name + ".cost"
@@ -204,6 +212,13 @@ def prepare_weights(state_dict, device):
                 sd[p + ".mlp_convs3.1.bias"].float(), bn1, bn2, w2(p + ".weightnet1.6.weight").reshape(-1),
                 _kmajor(w3)[m + Fc:], float(sd[p + ".weightnet1.6.bias"].reshape(-1)[0]))
             d["tc_blob"], d["tc_par"] = dev(blob), dev(par)
+        w42 = w2(p + ".mlp_convs4.1.weight")
+        d.update(Hab_img=img(torch.cat([wa[:, :D], ww[:, :D]], dim=0)), Gab_img=img(torch.cat([wa[:, D:], ww[:, D:]], dim=0)),
+                 W2a_img=img(w2(p + ".mlp_convs.1.weight")), W2w_img=img(w2(p + ".mlp_convs2.1.weight")),
+                 W3a_img=img(w3[:, :m]), W3b_img=img(w2(p + ".mlp_convs3.1.weight")), Wn1_img=img(wn1), Wn2_img=img(wn2),
+                 Hp_img=img(torch.cat([w4[:, :m], w4[:, 2 * m:2 * m + Fc]], dim=1)), G4_img=img(w4[:, m:2 * m]), W42_img=img(w42))
+        if Fc > 0:
+            d["H3_img"] = img(w3[:, m:m + Fc])
         d["W3a"] = d["W3"][:m]
         d["W3d"] = d["W3"][m + Fc:]
         d["W4d"] = d["W4"][2 * m + Fc:]
@@ -211,7 +226,7 @@ def prepare_weights(state_dict, device):
         i = 0
         while "%s.flow_mlp_convs.%d.composed_module.0.weight" % (p, i) in sd:
             k = "%s.flow_mlp_convs.%d.composed_module.0" % (p, i)
-            fm.append((dev(_kmajor(w2(k + ".weight"))), dev(sd[k + ".bias"].float()), sd[k + ".weight"].shape[0]))
+            fm.append((dev(_kmajor(w2(k + ".weight"))), dev(sd[k + ".bias"].float()), sd[k + ".weight"].shape[0], img(w2(k + ".weight"))))
             i += 1
         d["flow_mlp"] = fm
         W[name] = d
@@ -220,11 +235,24 @@ def prepare_weights(state_dict, device):
 
 # ------------------------------------------------------------------------------ point-major forward pieces
 
+def _tc():
+    return F_.USE_TC
+
+
 def set_abstraction_pm(w, npoint, nsample, xyz, feats):
     """xyz [B,N,3], feats [B,N,D] -> (new_xyz [B,S,3], new_feats [B,S,C3], fps_idx [B,S])."""
     fps_idx = F_.fps(xyz, npoint)
     new_xyz = F_.gather_rows(xyz, fps_idx)
     idx = F_.knn_idx(nsample, new_xyz, xyz)
+    D = feats.shape[-1]
+    if _tc():
+        # first conv split per point (Wg.feats once per source point), rows (n,s) formed on the fly inside the second
+        # conv's A operand, third conv + max over nsample in the epilogue: the grouped tensor never exists in HBM
+        G = F_.dense_tc(w["Wg_img"], w["C1"], D, x1=feats)
+        x2 = F_.dense_tc(w["W2_img"], w["C2"], w["C1"], G=G, b1=w["b1"], Wd1=w["Wd"], act1=ACT_RELU, idx=idx, pos_src=xyz,
+                         pos_q=new_xyz, bias=w["b2"], act=ACT_RELU)
+        out = F_.dense_tc(w["W3_img"], w["C3"], w["C2"], x1=x2, S=nsample, bias=w["b3"], act=ACT_RELU, epi=F_.EPI_MAX)
+        return new_xyz, out.view(xyz.shape[0], npoint, w["C3"]), fps_idx
     G = F_.linear(feats, w["Wg"], w["C1"])
     out = F_.group_mlp_max(G, idx, xyz, new_xyz, w["Wd"], w["b1"], w["W2"], w["b2"], w["C2"], w["W3"], w["b3"], w["C3"],
                            act=ACT_RELU)
@@ -234,6 +262,12 @@ def set_abstraction_pm(w, npoint, nsample, xyz, feats):
 def set_upconv_pm(w, nsample, pos1, pos2, feat1, feat2):
     """Feature propagation sparse (pos2, feat2) -> dense (pos1, feat1): [B,N1,mlp2[-1]]."""
     idx = F_.knn_idx(nsample, pos1, pos2)
+    if _tc():
+        G = F_.dense_tc(w["Wg_img"], w["C1"], feat2.shape[-1], x1=feat2)
+        pooled = F_.dense_tc(w["W2_img"], w["C2"], w["C1"], G=G, b1=w["b1"], Wd1=w["Wd"], act1=ACT_RELU, idx=idx, pos_src=pos2,
+                             pos_q=pos1, bias=w["b2"], act=ACT_RELU, epi=F_.EPI_MAX)
+        x = F_.dense_tc(w["M1_img"], w["MC1"], w["C2"] + feat1.shape[-1], x1=pooled, x2=feat1, bias=w["mb1"], act=ACT_RELU)
+        return F_.dense_tc(w["M2_img"], w["MC2"], w["MC1"], x1=x, bias=w["mb2"], act=ACT_RELU)
     G = F_.linear(feat2, w["Wg"], w["C1"])
     pooled = F_.group_mlp_max(G, idx, pos2, pos1, w["Wd"], w["b1"], w["W2"], w["b2"], w["C2"], act=ACT_RELU)
     x = F_.linear(pooled, w["M1"], w["MC1"], 0, feat1, w["C2"], bias=w["mb1"], act=ACT_RELU)
@@ -253,6 +287,31 @@ def point_warping_pm(pos1, pos2, flow1, k):
     return F_.interpolate(pos2, moved, flow1, idx, mode=1, clampv=10.0)
 
 
+def _cost_volume_wide_tc(w, Gab, Hab, H3, xyz1, xyz2, idx, idxw, m):
+    """m >= 128 (levels 2, 3): the dense layers as tensor-core GEMMs (rows = (point, neighbour)), the S x S attention and
+    the softmax-weighted forward cost on CUDA cores between them.  Same outputs as F_.cost_volume."""
+    B, N1, _ = xyz1.shape
+    L = ACT_LEAKY
+    br = []
+    for b_, (ii, w2i, b2) in enumerate(((idx, w["W2a_img"], w["b2a"]), (idxw, w["W2w_img"], w["b2w"]))):
+        br.append(F_.dense_tc(w2i, m, m, G=Gab, offG=b_ * m, H=Hab, offH=b_ * m, act1=L, idx=ii, bias=b2, act=L))
+    A, Aw = br                                                                  # [B,N1,16,m]
+    Amix, Awmix = F_.attention_mix(A, Aw)
+    outs = []
+    for rows, ii in ((A, idx), (Aw, idxw)):
+        c1 = F_.dense_tc(w["W3a_img"], m, m, x1=rows, idx=ii, pos_src=xyz2, pos_q=xyz1, Hq=H3, Wd2=w["W3d"], act=L)
+        outs.append(F_.dense_tc(w["W3b_img"], m, m, x1=c1, bias=w["b3b"], act=L))
+    C, Cw = outs
+    logits = []
+    for rows in (Amix, Awmix):
+        t1 = F_.dense_tc(w["Wn1_img"], m, m, x1=rows, bias=w["bn1"], act=ACT_RELU)
+        logits.append(F_.dense_tc(w["Wn2_img"], m // 2, m, x1=t1, bias=w["bn2"], act=ACT_RELU, epi=F_.EPI_DOT, wvec=w["wn3"],
+                                  b0=w["bn3"]))
+    g, gw = logits                                                              # [B,N1,16]
+    cost_fwd, cost_fwd_cm = F_.softmax_pool(g, C)
+    return cost_fwd, cost_fwd_cm, gw.view(B, N1 * 16), Cw.view(B, N1 * 16, m)
+
+
 def cost_volume_pm(w, xyz1, xyz2, xyz2w, f1a, f1b, f2a, f2b, sf=None, sf_feat=None):
     """PointConvTransFlowV2 on point-major inputs.  f1 = cat[f1a | f1b], f2 = cat[f2a | f2b] (b parts may be None).
     Returns (cost_fwd [B,N1,m], cost_bwd [B,N2,m], feats [B,N1,flow_mlp[-1]], flow [B,N1,3])."""
@@ -260,28 +319,44 @@ def cost_volume_pm(w, xyz1, xyz2, xyz2w, f1a, f1b, f2a, f2b, sf=None, sf_feat=No
     B, N1, _ = xyz1.shape
     N2 = xyz2.shape[1]
     ca = f1a.shape[-1]
+    tcp = _tc()
     idx = F_.knn_idx(16, xyz1, xyz2, offset=sf)
     idxw = F_.knn_idx(16, xyz1, xyz2 if xyz2w is None else xyz2w)
-    Hab = F_.linear(f1a, w["Wab"], 2 * m, 0, f1b, ca, bias=w["bab"])
-    Gab = F_.linear(f2a, w["Wab"], 2 * m, D, f2b, D + ca)
+    if tcp:
+        Hab = F_.dense_tc(w["Hab_img"], 2 * m, D, x1=f1a, x2=f1b, bias=w["bab"])
+        Gab = F_.dense_tc(w["Gab_img"], 2 * m, D, x1=f2a, x2=f2b)
+    else:
+        Hab = F_.linear(f1a, w["Wab"], 2 * m, 0, f1b, ca, bias=w["bab"])
+        Gab = F_.linear(f2a, w["Wab"], 2 * m, D, f2b, D + ca)
     if Fc > 0:
-        H3 = F_.linear(sf_feat, w["W3"], m, m, bias=w["b3"])
+        H3 = F_.dense_tc(w["H3_img"], m, Fc, x1=sf_feat, bias=w["b3"]) if tcp else F_.linear(sf_feat, w["W3"], m, m, bias=w["b3"])
     else:
         H3 = w["b3"].view(1, 1, m).expand(B, N1, m).contiguous()
-    cost_fwd, cost_fwd_cm, gw, Cw = F_.cost_volume(Gab, Hab, w, H3, xyz1, xyz2, idx, idxw, m)
+    if tcp and m != 64:
+        cost_fwd, cost_fwd_cm, gw, Cw = _cost_volume_wide_tc(w, Gab, Hab, H3, xyz1, xyz2, idx, idxw, m)
+    else:
+        cost_fwd, cost_fwd_cm, gw, Cw = F_.cost_volume(Gab, Hab, w, H3, xyz1, xyz2, idx, idxw, m)
     csr = F_.build_csr(idxw.view(B, N1 * 16), N2)
     cost_bwd = F_.segment_softmax_sum(gw, Cw, csr, N2)
     # mlp_convs4 input = cat[scrambled fwd | bwd[idx] | sf_feat | dir]; the "scramble" is the reference's .view of
     # the channel-major forward cost as [N1, m] rows (soflow.py:490): reinterpret, do not transpose
     scr = cost_fwd_cm.view(B, N1, m)
-    if Fc > 0:
-        Hp = F_.linear(scr, w["W4"], m, 0, sf_feat, 2 * m, bias=w["b4"])
+    if tcp:
+        Hp = F_.dense_tc(w["Hp_img"], m, m + Fc, x1=scr, x2=sf_feat if Fc > 0 else None, bias=w["b4"])
+        G4 = F_.dense_tc(w["G4_img"], m, m, x1=cost_bwd)
+        x = F_.dense_tc(w["W42_img"], m, m, G=G4, H=Hp, Wd1=w["W4d"], act1=ACT_LEAKY, idx=idx, pos_src=xyz2, pos_q=xyz1,
+                        bias=w["b42"], act=ACT_LEAKY, epi=F_.EPI_MAX)
+        for Wt, b, c, im in w["flow_mlp"]:
+            x = F_.dense_tc(im, c, x.shape[-1], x1=x, bias=b, act=ACT_LEAKY)
     else:
-        Hp = F_.linear(scr, w["W4"], m, 0, bias=w["b4"])
-    G4 = F_.linear(cost_bwd, w["W4"], m, m)
-    x = F_.group_mlp_max(G4, idx, xyz2, xyz1, w["W4d"], None, w["W42"], w["b42"], m, H=Hp, act=ACT_LEAKY)
-    for Wt, b, c in w["flow_mlp"]:
-        x = F_.linear(x, Wt, c, bias=b, act=ACT_LEAKY)
+        if Fc > 0:
+            Hp = F_.linear(scr, w["W4"], m, 0, sf_feat, 2 * m, bias=w["b4"])
+        else:
+            Hp = F_.linear(scr, w["W4"], m, 0, bias=w["b4"])
+        G4 = F_.linear(cost_bwd, w["W4"], m, m)
+        x = F_.group_mlp_max(G4, idx, xyz2, xyz1, w["W4d"], None, w["W42"], w["b42"], m, H=Hp, act=ACT_LEAKY)
+        for Wt, b, c, im in w["flow_mlp"]:
+            x = F_.linear(x, Wt, c, bias=b, act=ACT_LEAKY)
     flow = F_.linear(x, w["fc"], 3, bias=w["fcb"], clamp1=50.0, add=sf, clamp2=50.0)
     return cost_fwd, cost_bwd, x, flow
 
@@ -335,7 +410,7 @@ class TFlow(nn.Module):
         B = xyz1.shape[0]
         xyz = [torch.cat([xyz1, xyz2], dim=0).contiguous()]  # both clouds as one batch of 2B
         x = F_.linear(xyz[0], W["pc0"], 32, act=ACT_LEAKY)
-        feats = [F_.linear(x, W["pc1"], 32, act=ACT_LEAKY)]
+        feats = [F_.dense_tc(W["pc1_img"], 32, 32, x1=x, act=ACT_LEAKY) if _tc() else F_.linear(x, W["pc1"], 32, act=ACT_LEAKY)]
         fps = []
         for name, npoint, nsample in self.SA:
             nx, nf, fi = set_abstraction_pm(W[name], npoint, nsample, xyz[-1], feats[-1])
@@ -357,9 +432,13 @@ class TFlow(nn.Module):
             p2 = h2(xyz[lvl])
             coarse = upsample_pm(p1, p1s, flow, k_up)
             sf_feat = upsample_pm(p1, p1s, ff, k_up)
-            dcout = W[dc].shape[1]
-            cfu = F_.linear(upsample_pm(p1, p1s, cf, 3), W[dc], dcout, act=ACT_LEAKY)
-            cbu = F_.linear(upsample_pm(p1, p1s, cb, 3), W[dc], dcout, act=ACT_LEAKY)
+            dcin, dcout = W[dc].shape
+            if _tc():
+                cfu = F_.dense_tc(W[dc + "_img"], dcout, dcin, x1=upsample_pm(p1, p1s, cf, 3), act=ACT_LEAKY)
+                cbu = F_.dense_tc(W[dc + "_img"], dcout, dcin, x1=upsample_pm(p1, p1s, cb, 3), act=ACT_LEAKY)
+            else:
+                cfu = F_.linear(upsample_pm(p1, p1s, cf, 3), W[dc], dcout, act=ACT_LEAKY)
+                cbu = F_.linear(upsample_pm(p1, p1s, cb, 3), W[dc], dcout, act=ACT_LEAKY)
             warped = point_warping_pm(p1, p2, coarse, k_warp)
             cf, cb, ff, flow = cost_volume_pm(W[fr], p1, p2, warped, h1(up), cfu, h2(up), cbu, sf=coarse, sf_feat=sf_feat)
             flows.append(flow)

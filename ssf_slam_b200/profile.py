@@ -4,7 +4,7 @@ import torch
 
 from . import functional as F_
 
-_NAMES = ("linear", "gather_rows", "transpose", "fps", "knn_idx", "interpolate", "group_mlp_max", "cost_volume",
+_NAMES = ("linear", "dense_tc", "attention_mix", "softmax_pool", "gather_rows", "transpose", "fps", "knn_idx", "interpolate", "group_mlp_max", "cost_volume",
           "build_csr", "segment_softmax_sum", "frontend")
 _orig = {}
 _records = []
@@ -18,6 +18,10 @@ def _tag(name, args, kwargs):
             return "group_mlp_max[Nq=%d,S=%d,C1=%d]" % (args[1].shape[1], args[1].shape[2], args[0].shape[2])
         if name == "knn_idx":
             return "knn[k=%d,Nq=%d,Nr=%d]" % (args[0], args[1].shape[1], args[2].shape[1])
+        if name == "dense_tc":
+            rows = (k["x1"].numel() // k["x1"].shape[-1]) if k.get("x1") is not None else k["idx"].numel()
+            mode = "g" if k.get("G") is not None else "r"
+            return "dense_tc[%s,rows=%d,K=%d,N=%d,epi=%d]" % (mode, rows, args[2], args[1], k.get("epi", 0))
         if name == "fps":
             return "fps[N=%d,n=%d]" % (args[0].shape[1], args[1])
     except Exception:

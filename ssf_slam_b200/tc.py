@@ -37,3 +37,18 @@ def cost_volume_tc_pack(w2a, w2w, w3a, w3b, wn1, wn2, b2a, b2w, b3b, bn1, bn2, w
     params = torch.cat([b2a, b2w, b3b, bn1, bn2, wn3.reshape(-1), w3d.reshape(-1), torch.tensor([bn3, 0.0, 0.0, 0.0])]).float()
     assert blob.numel() * 4 == 5 * 32768 + 16384 and params.numel() == 516
     return blob, params.contiguous()
+
+
+def dense_image(w):
+    """w [N, K] (reference [Cout, Cin] orientation, BatchNorm folded) -> weight image of ``ssf_dense_tc``:
+    for every 256-column tile, for every 32-wide K chunk: [hi image | lo image] of the [Nt, 32] block."""
+    w = w.float().contiguous()
+    N, K = w.shape
+    assert K % 32 == 0 and N % 32 == 0 and (N <= 256 or N % 256 == 0)
+    hi, lo = split_tf32(w)
+    parts = []
+    for n0 in range(0, N, 256):
+        n1 = min(N, n0 + 256)
+        for k0 in range(0, K, 32):
+            parts += [kmajor_image(hi[n0:n1, k0:k0 + 32].contiguous()), kmajor_image(lo[n0:n1, k0:k0 + 32].contiguous())]
+    return torch.cat(parts).contiguous()

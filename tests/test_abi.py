@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_decls():
-    text = open(os.path.join(ROOT, "include", "ssf_b200.h")).read()
+    import glob
+    text = "".join(open(h).read() for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     decls = {}
     for m in re.finditer(r"([\w\s\*]+?)\b(ssf_\w+)\s*\(([^)]*)\)\s*;", text):
@@ -47,6 +48,13 @@ def test_ctypes_table_matches_header(built_lib):
     assert set(decls) == set(_native.SIGNATURES)
     for name, args in decls.items():
         assert "".join(_kind(a) for a in args) == _native.SIGNATURES[name][0], name
+
+
+def test_dense_args_struct_layout(built_lib):
+    """The ctypes mirror of ssf_dense_args has the size the compiled library sees."""
+    from ssf_slam_b200 import _native
+    lib = ctypes.CDLL(built_lib)
+    assert lib.ssf_dense_args_bytes() == ctypes.sizeof(_native.DenseArgs)
 
 
 def test_no_cpu_fallback():

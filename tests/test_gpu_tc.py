@@ -85,3 +85,59 @@ def test_cost_volume_tc_matches_simt(cv_weights, level, B, N1, N2, n_sm):
         err = float((r_ - g_).abs().max())
         print(level, name, "max-abs diff %.3g (scale %.3g)" % (err, scale))
         assert err < 2e-5 * scale, (name, err, scale)
+
+
+# ------------------------------------------------------------------ generic tensor-core dense layer
+
+def _act(x, act):
+    if act == 1:
+        return x.clamp(min=0)
+    if act == 2:
+        return torch.where(x > 0, x, 0.1 * x)
+    return x
+
+
+@pytest.mark.parametrize("rows,K,N,two_seg,act", [(128, 32, 32, False, 0), (1000, 96, 128, True, 2), (4096, 256, 256, False, 1),
+                                                  (300, 512, 256, True, 1), (2048, 256, 512, False, 1), (257, 64, 64, False, 2)])
+def test_dense_tc_rows(rows, K, N, two_seg, act):
+    from ssf_slam_b200 import functional as F_, tc
+    g = torch.Generator().manual_seed(rows + K + N)
+    X = torch.randn(rows, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    img = tc.dense_image(W).cuda()
+    if two_seg:
+        c1 = 64 if K > 64 else 32
+        y = F_.dense_tc(img, N, K, x1=X[:, :c1].contiguous().cuda(), x2=X[:, c1:].contiguous().cuda(), bias=b.cuda(), act=act)
+    else:
+        y = F_.dense_tc(img, N, K, x1=X.cuda(), bias=b.cuda(), act=act)
+    ref = _act(X.double() @ W.double().t() + b.double(), act)
+    err = float((y.cpu().double() - ref).abs().max())
+    print("dense_tc rows", rows, K, N, "max-abs err %.3g" % err)
+    assert err < 3e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,Nsrc,Nq,S,K,N,epi", [(2, 300, 100, 16, 64, 64, 0), (3, 200, 72, 8, 256, 512, 1), (2, 500, 333, 16, 128, 128, 1),
+                                                  (2, 128, 64, 16, 128, 64, 2)])
+def test_dense_tc_grouped(B, Nsrc, Nq, S, K, N, epi):
+    """Grouped first layer on the fly (gather + per-point block + direction term), per-point epilogue add, max / dot."""
+    from ssf_slam_b200 import functional as F_, tc
+    g = torch.Generator().manual_seed(B * 1000 + Nq)
+    r = lambda *s: torch.randn(*s, generator=g)
+    G, H, b1, Wd1 = r(B, Nsrc, K + 32), r(B, Nq, K), r(K), r(3, K) * 0.3
+    ps, pq = r(B, Nsrc, 3), r(B, Nq, 3)
+    idx = torch.randint(0, Nsrc, (B, Nq, S), generator=g, dtype=torch.int32)
+    W, bias, Hq, Wd2, wvec = r(N, K) / K ** 0.5, r(N), r(B, Nq, N), r(3, N) * 0.3, r(N)
+    li = idx.long()
+    bi = torch.arange(B)[:, None, None]
+    dirs = (ps[bi, li] - pq[:, :, None, :]).double()                              # [B,Nq,S,3]
+    A = _act(G[bi, li][..., 32:].double() + H[:, :, None, :].double() + b1.double() + dirs @ Wd1.double(), 2)
+    D = A @ W.double().t() + bias.double() + Hq[:, :, None, :].double() + dirs @ Wd2.double()
+    D = _act(D, 1)
+    cu = lambda t: t.cuda().contiguous()
+    y = F_.dense_tc(cu(tc.dense_image(W)), N, K, G=cu(G), offG=32, H=cu(H), b1=cu(b1), Wd1=cu(Wd1), act1=2, idx=cu(idx),
+                    pos_src=cu(ps), pos_q=cu(pq), bias=cu(bias), Hq=cu(Hq), Wd2=cu(Wd2), act=1, epi=epi, wvec=cu(wvec), b0=0.25)
+    ref = D if epi == 0 else (D.max(dim=2).values if epi == 1 else D @ wvec.double() + 0.25)
+    err = float((y.cpu().double() - ref).abs().max())
+    print("dense_tc grouped epi", epi, "max-abs err %.3g" % err, "scale %.3g" % float(ref.abs().max()))
+    assert y.shape == ref.shape and err < 3e-6 * max(1.0, float(ref.abs().max()))

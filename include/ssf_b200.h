@@ -45,6 +45,14 @@ int ssf_knn(int k, const float* query, const float* ref, int B, int Nq, int Nr, 
 int ssf_knn_offset(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,
                    float* dist, int* idx, void* stream);
 
+/* Same result as ssf_knn_offset, bit for bit, through a spatial index: `build` Morton-sorts each reference cloud into
+ * blocks of 32 points with bounding boxes (workspace of ssf_knn_blocks_workspace_floats(B,Nr) floats, Nr <= 16384),
+ * `search` walks the blocks nearest-first and stops when no remaining box can hold a closer point. */
+long long ssf_knn_blocks_workspace_floats(int B, int Nr);
+int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, void* stream);
+int ssf_knn_blocks_search(int k, const float* query, const float* query_add, const float* ws, int B, int Nq, int Nr,
+                          float* dist, int* idx, void* stream);
+
 /* three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3], idx[B,n,3]); ASF/utils/soflow.py:1241,1459 */
 int ssf_three_nn(const float* query, const float* ref, int B, int Nq, int Nr, float* dist, int* idx, void* stream);
 

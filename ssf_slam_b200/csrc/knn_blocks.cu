@@ -1,0 +1,281 @@
+// Exact k-nearest-neighbour search with spatial pruning: same results, bit for bit, as the brute-force `ssf_knn`
+// (distance = ((dx*dx)+(dy*dy))+(dz*dz) without FMA, order = (distance, index) lexicographic),
+// for `pointutils.knn / three_nn` call sites ASF/utils/utils.py:229,291 and ASF/utils/soflow.py:387-391,406,1243,1461.
+//
+// build : one CTA per reference cloud sorts the points along a 30-bit Morton curve (bitonic sort in shared memory),
+//         stores them as float4 (x, y, z, original index) and the bounding box of every block of 32 consecutive points.
+// search: one warp per query.  Lane l owns the lower bounds lb(q, box) of blocks l, l+32, ...; the warp repeatedly
+//         picks the unvisited block with the smallest bound, evaluates its 32 points in parallel (lane = point, one
+//         coalesced 512-byte load) and merges the survivors into a lane-distributed sorted list (lane j = j-th best).
+//         It stops when the smallest remaining bound exceeds the current k-th distance.
+// Exactness: every box bound is computed with the SAME rounded operations as the point distance and each of them
+// (fsub, fmul, fadd) is monotone, so bound <= distance of every point inside the box holds in floating point, not
+// just in exact arithmetic; blocks are skipped only on bound > kth (strict), so index ties are never lost.
+#include "ssf_common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int KB_BUILD_T = 1024;
+constexpr int KB_QPB = 64;   // queries per search CTA (8 warps x 8)
+
+__device__ __forceinline__ unsigned morton_spread(unsigned v) {   // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// ws layout per cloud (floats): pts4 [npad][4] | box_lo [nblk][4] | box_hi [nblk][4]
+__global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const float* __restrict__ ref, int Nr, int npow2, int npad,
+                                                                       int nblk, float* __restrict__ ws) {
+    extern __shared__ __align__(16) unsigned sm_u[];
+    unsigned* skey = sm_u;              // [npow2]
+    int* sval = reinterpret_cast<int*>(sm_u + npow2);   // [npow2]
+    __shared__ float sred[6][32];
+    __shared__ float sbb[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* rp = ref + (size_t)blockIdx.x * Nr * 3;
+    float* wsb = ws + (size_t)blockIdx.x * ((size_t)npad * 4 + (size_t)nblk * 8);
+    // cloud bounding box
+    float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int i = tid; i < Nr; i += KB_BUILD_T)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = rp[3 * i + c];
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if (lane == 0) {
+            sred[c][warp] = mn[c];
+            sred[3 + c][warp] = mx[c];
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float v = sred[tid][0];
+        for (int w = 1; w < KB_BUILD_T / 32; ++w) v = tid < 3 ? fminf(v, sred[tid][w]) : fmaxf(v, sred[tid][w]);
+        sbb[tid] = v;
+    }
+    __syncthreads();
+    float sc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ext = sbb[3 + c] - sbb[c];
+        sc[c] = ext > 0.f ? 1023.0f / ext : 0.f;
+    }
+    for (int i = tid; i < npow2; i += KB_BUILD_T) {
+        unsigned key = 0xFFFFFFFFu;
+        if (i < Nr) {
+            unsigned q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float t = (rp[3 * i + c] - sbb[c]) * sc[c];
+                q[c] = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
+            }
+            key = morton_spread(q[0]) | (morton_spread(q[1]) << 1) | (morton_spread(q[2]) << 2);
+        }
+        skey[i] = key;
+        sval[i] = i;
+    }
+    __syncthreads();
+    // bitonic sort on (key, val): val breaks key ties so the layout is a deterministic function of the cloud
+    for (int size = 2; size <= npow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (npow2 >> 1); t += KB_BUILD_T) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned ka = skey[lo], kb = skey[hi];
+                const int va = sval[lo], vb = sval[hi];
+                const bool a_gt_b = ka > kb || (ka == kb && va > vb);
+                if (a_gt_b == up) {
+                    skey[lo] = kb; skey[hi] = ka;
+                    sval[lo] = vb; sval[hi] = va;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // sorted points (padding: +inf coordinates, index INT_MAX -> never selected) and per-block boxes
+    float4* pts4 = reinterpret_cast<float4*>(wsb);
+    float4* blo = pts4 + npad;
+    float4* bhi = blo + nblk;
+    for (int i = tid; i < npad; i += KB_BUILD_T) {
+        float4 p = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(0x7fffffff));
+        float lo3[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi3[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        if (i < Nr) {
+            const int o = sval[i];
+            p = make_float4(rp[3 * o], rp[3 * o + 1], rp[3 * o + 2], __int_as_float(o));
+            lo3[0] = hi3[0] = p.x; lo3[1] = hi3[1] = p.y; lo3[2] = hi3[2] = p.z;
+        }
+        pts4[i] = p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo3[c] = fminf(lo3[c], __shfl_xor_sync(0xffffffffu, lo3[c], o));
+                hi3[c] = fmaxf(hi3[c], __shfl_xor_sync(0xffffffffu, hi3[c], o));
+            }
+        if (lane == 0) {
+            blo[i >> 5] = make_float4(lo3[0], lo3[1], lo3[2], 0.f);
+            bhi[i >> 5] = make_float4(hi3[0], hi3[1], hi3[2], 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ bool key_less(float d, int i, float kd, int ki) { return d < kd || (d == kd && i < ki); }
+
+template <int NBL>
+__global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
+                                                                const float* __restrict__ ws, int Nq, int npad, int nblk,
+                                                                float* __restrict__ dist, int* __restrict__ idx) {
+    extern __shared__ __align__(16) float4 sbox[];   // [nblk] lo | [nblk] hi
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const float* wsb = ws + (size_t)b * ((size_t)npad * 4 + (size_t)nblk * 8);
+    const float4* P = reinterpret_cast<const float4*>(wsb);
+    {
+        const float4* src = P + npad;
+        for (int i = tid; i < 2 * nblk; i += 256) sbox[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int q_end = min(Nq, (int)(blockIdx.x + 1) * KB_QPB);
+    for (int qi = blockIdx.x * KB_QPB + warp; qi < q_end; qi += 8) {
+        const float* qp = query + ((size_t)b * Nq + qi) * 3;
+        float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        if (qadd != nullptr) {
+            const float* ap = qadd + ((size_t)b * Nq + qi) * 3;
+            qx = __fadd_rn(qx, __ldg(ap));
+            qy = __fadd_rn(qy, __ldg(ap + 1));
+            qz = __fadd_rn(qz, __ldg(ap + 2));
+        }
+        float lb[NBL];
+#pragma unroll
+        for (int s = 0; s < NBL; ++s) {
+            const int blk = s * 32 + lane;
+            lb[s] = CUDART_INF_F;
+            if (blk < nblk) {
+                const float4 lo = sbox[blk], hi = sbox[nblk + blk];
+                const float gx = fmaxf(0.f, fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)));
+                const float gy = fmaxf(0.f, fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)));
+                const float gz = fmaxf(0.f, fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)));
+                lb[s] = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+            }
+        }
+        float list_d = CUDART_INF_F, kth_d = CUDART_INF_F;
+        int list_i = 0x7fffffff, kth_i = 0x7fffffff;
+        while (true) {
+            float best = lb[0];
+            int bs = 0;
+#pragma unroll
+            for (int s = 1; s < NBL; ++s)
+                if (lb[s] < best) {
+                    best = lb[s];
+                    bs = s;
+                }
+            int bblk = bs * 32 + lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bblk, o);
+                if (ob < best || (ob == best && ok < bblk)) {
+                    best = ob;
+                    bblk = ok;
+                }
+            }
+            if (best == CUDART_INF_F || best > kth_d) break;   // nothing left, or no remaining box can hold a better point
+#pragma unroll
+            for (int s = 0; s < NBL; ++s)
+                if (s == (bblk >> 5) && lane == (bblk & 31)) lb[s] = CUDART_INF_F;
+            const float4 p = __ldg(P + (size_t)bblk * 32 + lane);
+            const float d = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z);
+            const int pi = __float_as_int(p.w);
+            unsigned mask = __ballot_sync(0xffffffffu, key_less(d, pi, kth_d, kth_i));
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float cd = __shfl_sync(0xffffffffu, d, src);
+                const int ci = __shfl_sync(0xffffffffu, pi, src);
+                if (!key_less(cd, ci, kth_d, kth_i)) continue;   // warp-uniform: the k-th key tightened meanwhile
+                const int pos = __popc(__ballot_sync(0xffffffffu, key_less(list_d, list_i, cd, ci)));
+                const float ud = __shfl_up_sync(0xffffffffu, list_d, 1);
+                const int ui = __shfl_up_sync(0xffffffffu, list_i, 1);
+                if (lane == pos) {
+                    list_d = cd;
+                    list_i = ci;
+                } else if (lane > pos) {
+                    list_d = ud;
+                    list_i = ui;
+                }
+                kth_d = __shfl_sync(0xffffffffu, list_d, k - 1);
+                kth_i = __shfl_sync(0xffffffffu, list_i, k - 1);
+            }
+        }
+        if (lane < k) {
+            const size_t o = ((size_t)b * Nq + qi) * k + lane;
+            idx[o] = list_i;
+            if (dist != nullptr) dist[o] = __fsqrt_rn(list_d);
+        }
+    }
+}
+
+inline int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+// floats of workspace for B reference clouds of Nr points
+extern "C" long long ssf_knn_blocks_workspace_floats(int B, int Nr) {
+    const long long npad = ((long long)Nr + 31) / 32 * 32, nblk = npad / 32;
+    return (long long)B * (npad * 4 + nblk * 8);
+}
+
+extern "C" int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, void* stream) {
+    if (B <= 0 || Nr <= 0) return ssf_arg_error("knn_blocks_build: empty input");
+    if (Nr > 16384) return ssf_arg_error("knn_blocks_build: at most 16384 reference points (larger clouds use ssf_knn)");
+    const int npow2 = next_pow2(Nr), npad = (Nr + 31) / 32 * 32, nblk = npad / 32;
+    const size_t smem = (size_t)npow2 * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(knn_blocks_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+        if (e != cudaSuccess) return ssf_set_error(e);
+        attr_set = true;
+    }
+    knn_blocks_build_kernel<<<B, KB_BUILD_T, smem, (cudaStream_t)stream>>>(ref, Nr, npow2, npad, nblk, ws);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+extern "C" int ssf_knn_blocks_search(int k, const float* query, const float* query_add, const float* ws, int B, int Nq, int Nr,
+                                     float* dist, int* idx, void* stream) {
+    if (B <= 0 || Nq <= 0) return ssf_arg_error("knn_blocks_search: empty input");
+    if (k <= 0 || k > 32) return ssf_arg_error("knn: k must be in [1,32]");
+    if (k > Nr) return ssf_arg_error("knn: k exceeds the number of reference points");
+    if (Nr > 16384) return ssf_arg_error("knn_blocks_search: at most 16384 reference points");
+    const int npad = (Nr + 31) / 32 * 32, nblk = npad / 32;
+    const size_t smem = (size_t)nblk * 32;
+    dim3 grid((Nq + KB_QPB - 1) / KB_QPB, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nblk <= 64)
+        knn_blocks_search_kernel<2><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+    else if (nblk <= 256)
+        knn_blocks_search_kernel<8><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+    else
+        knn_blocks_search_kernel<16><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}

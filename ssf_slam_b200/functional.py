@@ -134,11 +134,40 @@ def fps(xyz, npoint):
     return out
 
 
+# reference clouds at least this large go through the Morton-block search (csrc/knn_blocks.cu); smaller ones through the
+# brute-force scan.  Both return identical indices.
+KNN_BLOCKS_MIN_REF = 512
+KNN_BLOCKS_MAX_REF = 16384
+_knn_cache = {}
+
+
+def knn_cache_clear():
+    """Drops the per-cloud search structures (call at the start of every forward: clouds are new tensors each time)."""
+    _knn_cache.clear()
+
+
+def _knn_blocks(ref):
+    key = (ref.data_ptr(), tuple(ref.shape), tuple(ref.stride()))
+    hit = _knn_cache.get(key)
+    if hit is None:
+        B, Nr, _ = ref.shape
+        ws = torch.empty(int(nat.lib().ssf_knn_blocks_workspace_floats(B, Nr)), dtype=torch.float32, device=ref.device)
+        nat.check(nat.lib().ssf_knn_blocks_build(nat.ptr(ref), B, Nr, nat.ptr(ws), nat.stream()))
+        hit = (ref, ws)  # keeping `ref` alive pins its storage, so the pointer in the key cannot be recycled
+        _knn_cache[key] = hit
+    return hit[1]
+
+
 def knn_idx(k, query, ref, offset=None):
     """Indices only (every hot call site discards the distances): i32 [B,Nq,k]."""
     B, Nq, _ = query.shape
     Nr = ref.shape[1]
     idx = torch.empty(B, Nq, k, dtype=torch.int32, device=query.device)
+    if KNN_BLOCKS_MIN_REF <= Nr <= KNN_BLOCKS_MAX_REF:
+        ws = _knn_blocks(ref)
+        nat.check(nat.lib().ssf_knn_blocks_search(k, nat.ptr(query), nat.ptr(offset), nat.ptr(ws), B, Nq, Nr, None, nat.ptr(idx),
+                                                  nat.stream()))
+        return idx
     nat.check(nat.lib().ssf_knn_offset(k, nat.ptr(query), nat.ptr(offset), nat.ptr(ref), B, Nq, Nr, None, nat.ptr(idx),
                                        nat.stream()))
     return idx

@@ -406,6 +406,7 @@ class TFlow(nn.Module):
     def forward_pm(self, xyz1, xyz2):
         """xyz1, xyz2 f32 [B,N,3] (point-major, CUDA) -> (flows pm [[B,N,3],[B,2048,3],[B,512,3],[B,256,3]], fps idx x3)."""
         nat.require_device()
+        F_.knn_cache_clear()
         W = self.weights(xyz1.device)
         B = xyz1.shape[0]
         xyz = [torch.cat([xyz1, xyz2], dim=0).contiguous()]  # both clouds as one batch of 2B
@@ -442,6 +443,7 @@ class TFlow(nn.Module):
             warped = point_warping_pm(p1, p2, coarse, k_warp)
             cf, cb, ff, flow = cost_volume_pm(W[fr], p1, p2, warped, h1(up), cfu, h2(up), cbu, sf=coarse, sf_feat=sf_feat)
             flows.append(flow)
+        F_.knn_cache_clear()
         return flows[::-1], [f[:B] for f in fps[:3]]
 
     @torch.no_grad()

@@ -19,9 +19,9 @@ def _tag(name, args, kwargs):
         if name == "knn_idx":
             return "knn[k=%d,Nq=%d,Nr=%d]" % (args[0], args[1].shape[1], args[2].shape[1])
         if name == "dense_tc":
-            rows = (k["x1"].numel() // k["x1"].shape[-1]) if k.get("x1") is not None else k["idx"].numel()
-            mode = "g" if k.get("G") is not None else "r"
-            return "dense_tc[%s,rows=%d,K=%d,N=%d,epi=%d]" % (mode, rows, args[2], args[1], k.get("epi", 0))
+            rows = (kwargs["x1"].numel() // kwargs["x1"].shape[-1]) if kwargs.get("x1") is not None else kwargs["idx"].numel()
+            mode = "g" if kwargs.get("G") is not None else "r"
+            return "dense_tc[%s,rows=%d,K=%d,N=%d,epi=%d]" % (mode, rows, args[2], args[1], kwargs.get("epi", 0))
         if name == "fps":
             return "fps[N=%d,n=%d]" % (args[0].shape[1], args[1])
     except Exception:

@@ -140,3 +140,29 @@ def test_scatter(L, C, n):
     # run-to-run determinism (no atomics in the accumulation)
     ss2 = scatter.scatter_sum(_cuda(src), _cuda(index), dim=1).cpu()
     assert torch.equal(ss, ss2)
+
+
+@pytest.mark.parametrize("B,Nq,Nr,k,dup,off", [(2, 700, 1000, 16, False, False), (2, 2048, 8192, 16, True, True), (1, 8192, 8192, 7, True, False),
+                                               (3, 513, 2048, 3, False, True), (1, 300, 16384, 5, False, False), (2, 64, 33, 16, False, False)])
+def test_knn_blocks_equals_brute_force(B, Nq, Nr, k, dup, off):
+    """The Morton-block search returns exactly the brute-force scan's indices and distances (ties included)."""
+    import torch
+    from ssf_slam_b200 import _native as nat
+    g = torch.Generator().manual_seed(Nq + Nr + k)
+    ref = torch.randn(B, Nr, 3, generator=g) * torch.tensor([30.0, 20.0, 2.0])
+    if dup:  # duplicated points: exact distance ties, the index order is observable
+        ref[:, Nr // 2:] = ref[:, :Nr - Nr // 2]
+    query = ref[:, torch.randperm(Nr, generator=g)[:Nq] % Nr].clone() if Nq <= Nr else torch.randn(B, Nq, 3, generator=g) * 20
+    query[:, ::3] += torch.randn(B, (Nq + 2) // 3, 3, generator=g)
+    qadd = (torch.randn(B, Nq, 3, generator=g) * 0.5).cuda() if off else None
+    ref, query = ref.cuda().contiguous(), query.cuda().contiguous()
+    L = nat.lib()
+    d0 = torch.empty(B, Nq, k, device="cuda"); i0 = torch.empty(B, Nq, k, dtype=torch.int32, device="cuda")
+    d1 = torch.full((B, Nq, k), -1.0, device="cuda"); i1 = torch.full((B, Nq, k), -1, dtype=torch.int32, device="cuda")
+    nat.check(L.ssf_knn_offset(k, nat.ptr(query), nat.ptr(qadd), nat.ptr(ref), B, Nq, Nr, nat.ptr(d0), nat.ptr(i0), nat.stream()))
+    ws = torch.empty(int(L.ssf_knn_blocks_workspace_floats(B, Nr)), device="cuda")
+    nat.check(L.ssf_knn_blocks_build(nat.ptr(ref), B, Nr, nat.ptr(ws), nat.stream()))
+    nat.check(L.ssf_knn_blocks_search(k, nat.ptr(query), nat.ptr(qadd), nat.ptr(ws), B, Nq, Nr, nat.ptr(d1), nat.ptr(i1), nat.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(i0, i1)
+    assert torch.equal(d0, d1)

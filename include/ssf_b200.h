@@ -101,9 +101,11 @@ int ssf_gather_rows(const float* src, const int* idx, int B, int N, int M, int C
 int ssf_transpose(const float* in, int B, int R, int C, float* out, void* stream);
 
 /* UpsampleFlow.forward (mode 0, clamp 100; ASF/utils/soflow.py:1443-1475) and the interpolation + warp of
- * PointWarping.forward (mode 1, clamp 10; ASF/utils/soflow.py:1244-1257), given the neighbour indices */
-int ssf_interpolate(const float* query, const float* src_pos, const float* src_val, const int* idx, int B, int N,
-                    int M, int C, int k, int mode, float clampv, float* out, void* stream);
+ * PointWarping.forward (mode 1, clamp 10; ASF/utils/soflow.py:1244-1257), given the neighbour indices.  idx rows are
+ * ld_idx apart and their first k entries are used: the k nearest neighbours are a prefix of any longer (distance, index)
+ * ordered list, so one kNN call serves every interpolation between the same two clouds. */
+int ssf_interpolate(const float* query, const float* src_pos, const float* src_val, const int* idx, int ld_idx, int B,
+                    int N, int M, int C, int k, int mode, float clampv, float* out, void* stream);
 
 /* gather -> MLP -> max over S: PointNetSetAbstraction.forward (ASF/utils/utils.py:231-247), the mlp1 half of
  * PointNetSetUpConv.forward (:296-307) and mlp_convs4 + max of PointConvTransFlowV2 (ASF/utils/soflow.py:489-509).

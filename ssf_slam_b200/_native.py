@@ -41,7 +41,7 @@ SIGNATURES = {
     "ssf_linear": ("piipiipiiipiiifpifpip", _I),
     "ssf_gather_rows": ("ppiiiipp", _I),
     "ssf_transpose": ("piiipp", _I),
-    "ssf_interpolate": ("ppppiiiiiifpp", _I),
+    "ssf_interpolate": ("ppppiiiiiiifpp", _I),
     "ssf_group_mlp_max": ("ppppppp" + "ppi" + "ppi" + "iiiiii" + "pp", _I),
     "ssf_cost_volume": ("p" * 16 + "f" + "pppp" + "iiii" + "pppp" + "p", _I),
     "ssf_cost_volume_tc": ("p" * 9 + "iiii" + "pppp" + "ip", _I),

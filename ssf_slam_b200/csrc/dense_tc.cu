@@ -2,27 +2,42 @@
 // ASF/utils/soflow.py:397-451,460-461,501-513): Y[rows, N] = epilogue(A[rows, K] . W[N, K]^T) on tcgen05
 // `kind::tf32` with the fp32-faithful 3xTF32 split (tc_common.cuh), fp32 accumulators in TMEM.
 //
-// One CTA computes a 128-row x (<= 256)-column tile.  The K dimension is streamed in chunks of 32:
-//   * A chunk: produced by the "row" threads (thread = row = TMEM lane).  Either plain rows of one or two
-//     concatenated inputs, or the *grouped first layer* evaluated on the fly,
-//         A[(b,n,s), c] = act1(G[b, idx[b,n,s], offG + c] + H[b, n, offH + c] + b1[c] + Wd1[:, c] . (pos_src[idx] - pos_q[n])),
-//     so a gathered neighbourhood never exists in HBM.  The chunk is split into (hi, lo) TF32 halves and written
-//     to TMEM with tcgen05.st; two row warpgroups alternate chunks so their global-load latencies overlap.
-//   * W chunk: the host pre-arranges, per 32-wide K chunk, the [N x 32] hi and lo images in the no-swizzle
-//     K-major UMMA layout; one cp.async.bulk (TMA) per chunk through a 3-stage shared-memory ring.
-//   * one thread issues 12 MMAs per chunk (3 passes x 4 K-steps of 8).
-// Epilogues (thread = row, the two warpgroups take half of the columns each):
-//   STORE: y[row, :] = act(D + bias [+ Hq[row / S] + Wd2 . dir(row)])
-//   MAX  : y[row / S, :] = max over the S rows of a point of the same expression   (S in {8, 16})
-//   DOT  : y[row] = wvec . act(D + bias) + b0                                        (weightnet1's last conv)
+// Persistent kernel: grid = (min(row tiles, SMs), column tiles of <= 256); every CTA walks 128-row tiles.  Roles:
+//   warps 0-3 / 4-7  two A-producer warpgroups (thread = row = TMEM lane) taking alternate tiles.  A is streamed in
+//                    K chunks of 32: either plain rows of one or two concatenated inputs, or the *grouped first layer*
+//                    evaluated on the fly,
+//                       A[(b,n,s), c] = act1(G[b, idx[b,n,s], offG + c] + H[b, n, offH + c] + b1[c] + Wd1[:, c] . dir),
+//                    so a gathered neighbourhood never exists in HBM.  Each chunk is split into (hi, lo) TF32 halves and
+//                    written to a ring of TMEM stages with tcgen05.st.  Neighbour indices, positions and the next
+//                    chunk's rows are prefetched one step ahead in registers.
+//   warps 8-11       epilogue (thread = row): tcgen05.ld of the accumulator, then
+//                       STORE: y[row, :] = act(D + bias [+ Hq[row / S] + Wd2 . dir(row)])
+//                       MAX  : y[row / S, :] = max over the S rows of a point (S in {8, 16}; butterfly over lanes)
+//                       DOT  : y[row] = wvec . act(D + bias) + b0                      (weightnet1's last conv)
+//   warp 12          one thread issues the MMAs (12 per chunk: 3 passes x 4 K-steps of 8)
+//   warp 13          one thread brings the weight image in with cp.async.bulk (TMA): the host pre-arranges, per 32-wide
+//                    K chunk, the [N x 32] hi and lo images in the no-swizzle K-major UMMA layout.  Layers whose image
+//                    fits in shared memory keep it resident for the whole kernel; wider ones stream it through a ring.
+// The accumulator is double buffered in TMEM when 2 N + 256 <= 512 columns, so the epilogue of one tile overlaps the
+// MMAs of the next.
 #include "tc_common.cuh"
 #include "ssf_dense.h"
 
 namespace {
 
-constexpr int KC = 32;         // K chunk
-constexpr int WSTAGES = 3;
-constexpr int DT_THREADS = 320;
+constexpr int KC = 32;                    // K chunk
+constexpr int AS = 4;                     // TMEM A stages (64 columns each: hi | lo)
+constexpr int DT_THREADS = 448;
+constexpr int W_SMEM_MAX = 192 * 1024;    // bytes of shared memory for weight images
+
+struct DenseCfg {
+    int Nt;          // columns of a CTA tile
+    int nk;          // K chunks
+    int nstage;      // weight stages in shared memory
+    int resident;    // whole image resident (nk <= nstage)
+    int nd;          // accumulator buffers
+    int n_tiles;     // row tiles
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
@@ -43,253 +58,340 @@ __device__ __forceinline__ void ldg8(const float* p, float (&o)[8]) {
     const float4 x = __ldg(reinterpret_cast<const float4*>(p)), y = __ldg(reinterpret_cast<const float4*>(p) + 1);
     o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
 }
+__device__ __forceinline__ void lds8(const float* p, float (&o)[8]) {
+    const float4 x = *reinterpret_cast<const float4*>(p), y = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
+}
 
-__global__ void __launch_bounds__(DT_THREADS) dense_tc_kernel(ssf_dense_args a, int n_astage, int tmem_cols) {
+// per-row geometry of a tile
+struct RowCtx {
+    long long row;    // global row (may be >= rows in the last tile)
+    long long rowc;   // clamped
+    long long pt;     // flat point index (row / S)
+    long long srow;   // flat source row b * Nsrc + idx
+    float px, py, pz; // pos_src[srow]
+    float qx, qy, qz; // pos_q[pt]
+};
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int Nt = a.N < 256 ? a.N : 256;                 // columns of this CTA's tile
-    const int n0 = blockIdx.y * 256;                       // first output column
+    const int Nt = cfg.Nt, nk = cfg.nk;
+    const int n0 = blockIdx.y * 256;                       // first output column of this CTA
     const uint32_t wchunk = (uint32_t)Nt * KC * 4 * 2;     // bytes of one weight chunk (hi + lo)
     uint8_t* sW = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WSTAGES * wchunk);
-    uint64_t* w_full = bars;              // [WSTAGES]
-    uint64_t* w_empty = bars + WSTAGES;   // [WSTAGES]
-    uint64_t* a_ready = bars + 2 * WSTAGES;      // [4]
-    uint64_t* a_empty = bars + 2 * WSTAGES + 4;  // [4]
-    uint64_t* d_ready = bars + 2 * WSTAGES + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WSTAGES + 9);
+    float* sPar = reinterpret_cast<float*>(smem + (size_t)cfg.nstage * wchunk);
+    float* sB1 = sPar;                 // [K]
+    float* sWd1 = sB1 + a.K;           // [3][K]
+    float* sBias = sWd1 + 3 * a.K;     // [Nt]
+    float* sWd2 = sBias + Nt;          // [3][Nt]
+    float* sWvec = sWd2 + 3 * Nt;      // [Nt]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sWvec + Nt);
+    uint64_t* w_full = bars;                        // [nstage] (<= 16)
+    uint64_t* w_empty = bars + 16;                  // [nstage]
+    uint64_t* a_ready = bars + 32;                  // [AS]
+    uint64_t* a_empty = bars + 36;                  // [AS]
+    uint64_t* d_full = bars + 40;                   // [2]
+    uint64_t* d_empty = bars + 42;                  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nk = a.K / KC;
-    if (warp == 8) tc_alloc(tmem_slot, (uint32_t)tmem_cols);
+    if (warp == 12) tc_alloc(tmem_slot, 512);
     if (tid == 0) {
-        for (int i = 0; i < WSTAGES; ++i) {
+        for (int i = 0; i < cfg.nstage; ++i) {
             ssf_mbar_init(&w_full[i], 1);
             ssf_mbar_init(&w_empty[i], 1);
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < AS; ++i) {
             ssf_mbar_init(&a_ready[i], 128);
             ssf_mbar_init(&a_empty[i], 1);
         }
-        ssf_mbar_init(d_ready, 1);
+        for (int i = 0; i < 2; ++i) {
+            ssf_mbar_init(&d_full[i], 1);
+            ssf_mbar_init(&d_empty[i], 128);
+        }
         ssf_mbar_fence_init();
+    }
+    for (int i = tid; i < a.K; i += DT_THREADS) {
+        sB1[i] = a.b1 ? __ldg(a.b1 + i) : 0.f;
+        for (int c = 0; c < 3; ++c) sWd1[c * a.K + i] = a.Wd1 ? __ldg(a.Wd1 + c * a.K + i) : 0.f;
+    }
+    for (int i = tid; i < Nt; i += DT_THREADS) {
+        sBias[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
+        for (int c = 0; c < 3; ++c) sWd2[c * Nt + i] = a.Wd2 ? __ldg(a.Wd2 + c * a.N + n0 + i) : 0.f;
+        sWvec[i] = a.wvec ? __ldg(a.wvec + n0 + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t a_col0 = (uint32_t)(tmem_cols == 512 ? 256 : 128);   // A stages live after the D columns
+    const uint32_t a_col0 = (uint32_t)(cfg.nd * Nt);
+    const int n_my = ((int)blockIdx.x < cfg.n_tiles) ? (cfg.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp == 9) {
+    if (warp == 13) {
         if (lane == 0) {   // ---- weight producer
             const uint8_t* wsrc = static_cast<const uint8_t*>(a.wimg) + (size_t)blockIdx.y * nk * wchunk;
-            for (int kc = 0; kc < nk; ++kc) {
-                const int st = kc % WSTAGES;
-                if (kc >= WSTAGES) ssf_mbar_wait(&w_empty[st], (uint32_t)((kc / WSTAGES - 1) & 1));
-                ssf_mbar_expect_tx(&w_full[st], wchunk);
-                ssf_bulk_g2s(sW + st * wchunk, wsrc + (size_t)kc * wchunk, wchunk, &w_full[st]);
+            if (cfg.resident) {
+                if (n_my > 0)
+                    for (int kc = 0; kc < nk; ++kc) {
+                        ssf_mbar_expect_tx(&w_full[kc], wchunk);
+                        ssf_bulk_g2s(sW + (size_t)kc * wchunk, wsrc + (size_t)kc * wchunk, wchunk, &w_full[kc]);
+                    }
+            } else {
+                const int total = n_my * nk;
+                for (int g = 0; g < total; ++g) {
+                    const int st = g % cfg.nstage;
+                    if (g >= cfg.nstage) ssf_mbar_wait(&w_empty[st], (uint32_t)((g / cfg.nstage - 1) & 1));
+                    ssf_mbar_expect_tx(&w_full[st], wchunk);
+                    ssf_bulk_g2s(sW + (size_t)st * wchunk, wsrc + (size_t)(g % nk) * wchunk, wchunk, &w_full[st]);
+                }
             }
         }
         __syncwarp();
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         if (lane == 0) {   // ---- MMA issuer
             const uint32_t idesc = tc_idesc_tf32(128, Nt);
             const uint32_t lbo = (uint32_t)(Nt / 8) * 128;
-            uint32_t acc = 0;
-            for (int kc = 0; kc < nk; ++kc) {
-                const int ws = kc % WSTAGES, as = kc % n_astage;
-                ssf_mbar_wait(&w_full[ws], (uint32_t)((kc / WSTAGES) & 1));
-                ssf_mbar_wait(&a_ready[as], (uint32_t)((kc / n_astage) & 1));
-                tc_fence_after();
-                const uint32_t w_hi = ssf_smem_u32(sW + ws * wchunk), w_lo = w_hi + (uint32_t)Nt * KC * 4;
-                const uint32_t a_hi = tmem + a_col0 + as * 64, a_lo = a_hi + 32;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t aa = pass == 0 ? a_lo : a_hi;
-                    const uint32_t ww = pass == 1 ? w_lo : w_hi;
-#pragma unroll
-                    for (int ks = 0; ks < KC / 8; ++ks) {
-                        tc_mma_ts(tmem, aa + ks * 8, tc_smem_desc(ww + ks * 2 * lbo, lbo, 128), idesc, acc);
-                        acc = 1;
-                    }
+            for (int it = 0; it < n_my; ++it) {
+                const int db = it % cfg.nd;
+                if (it >= cfg.nd) {
+                    ssf_mbar_wait(&d_empty[db], (uint32_t)((it / cfg.nd - 1) & 1));
+                    tc_fence_after();
                 }
-                tc_commit(&a_empty[as]);
-                tc_commit(&w_empty[ws]);
+                const uint32_t d_tmem = tmem + (uint32_t)(db * Nt);
+                for (int kc = 0; kc < nk; ++kc) {
+                    const int g = it * nk + kc;
+                    const int j = (it >> 1) * nk + kc;                // chunk count of the producing warpgroup
+                    const int ws = cfg.resident ? kc : g % cfg.nstage, as = (it & 1) * 2 + (j & 1);
+                    if (cfg.resident) {
+                        if (it == 0) ssf_mbar_wait(&w_full[ws], 0);
+                    } else {
+                        ssf_mbar_wait(&w_full[ws], (uint32_t)((g / cfg.nstage) & 1));
+                    }
+                    ssf_mbar_wait(&a_ready[as], (uint32_t)((j >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t w_hi = ssf_smem_u32(sW + (size_t)ws * wchunk), w_lo = w_hi + (uint32_t)Nt * KC * 4;
+                    const uint32_t a_hi = tmem + a_col0 + as * 64, a_lo = a_hi + 32;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t aa = pass == 0 ? a_lo : a_hi;
+                        const uint32_t ww = pass == 1 ? w_lo : w_hi;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks)
+                            tc_mma_ts(d_tmem, aa + ks * 8, tc_smem_desc(ww + ks * 2 * lbo, lbo, 128), idesc,
+                                      (kc > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&a_empty[as]);
+                    if (!cfg.resident) tc_commit(&w_empty[ws]);
+                }
+                tc_commit(&d_full[db]);
             }
-            tc_commit(d_ready);
         }
         __syncwarp();
-    } else {
-        // ---- row threads: A producer, then epilogue
+    } else if (warp < 8) {
+        // ---- A producers: warpgroup wg takes tiles it = wg, wg + 2, ...
         const int wg = warp >> 2;
         const int r = tid & 127;
-        const long long row = (long long)blockIdx.x * 128 + r;
-        const bool valid = row < a.rows;
-        const long long rowc = valid ? row : (long long)a.rows - 1;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        // grouped-row geometry (only when S > 0)
-        long long pt = 0;        // flat point index b*Nq + n
-        long long srow = 0;      // flat source row b*Nsrc + idx
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        if (a.S > 0) {
-            pt = rowc / a.S;
-            if (a.idx != nullptr) {
-                const long long b = pt / a.Nq;
-                srow = b * a.Nsrc + __ldg(a.idx + rowc);
-                if (a.pos_src != nullptr) {
-                    const float* ps = a.pos_src + srow * 3;
-                    const float* pq = a.pos_q + pt * 3;
-                    dx = __ldg(ps) - __ldg(pq);
-                    dy = __ldg(ps + 1) - __ldg(pq + 1);
-                    dz = __ldg(ps + 2) - __ldg(pq + 2);
+        const bool grouped = a.S > 0 && a.idx != nullptr;
+        const bool need_dir = grouped && a.Wd1 != nullptr;
+
+        auto row_of = [&](int it) -> long long { return ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r; };
+        auto clampr = [&](long long row) -> long long { return row < a.rows ? row : a.rows - 1; };
+        auto load_idx = [&](int it) -> int {   // neighbour index of this thread's row in tile `it`
+            if (!grouped || it >= n_my) return 0;
+            return __ldg(a.idx + clampr(row_of(it)));
+        };
+        auto make_ctx = [&](int it, int id) -> RowCtx {   // issues the position loads (if needed)
+            RowCtx c;
+            c.row = row_of(it < n_my ? it : n_my - 1);
+            c.rowc = clampr(c.row);
+            c.pt = a.S > 0 ? c.rowc / a.S : 0;
+            c.srow = 0;
+            c.px = c.py = c.pz = c.qx = c.qy = c.qz = 0.f;
+            if (grouped) {
+                const long long b = c.pt / a.Nq;
+                c.srow = b * a.Nsrc + id;
+                if (need_dir) {
+                    const float* ps = a.pos_src + c.srow * 3;
+                    const float* pq = a.pos_q + c.pt * 3;
+                    c.px = __ldg(ps); c.py = __ldg(ps + 1); c.pz = __ldg(ps + 2);
+                    c.qx = __ldg(pq); c.qy = __ldg(pq + 1); c.qz = __ldg(pq + 2);
                 }
             }
-        }
-        for (int kc = wg; kc < nk; kc += 2) {
-            const int as = kc % n_astage;
+            return c;
+        };
+        auto issue_loads = [&](const RowCtx& c, int kc, float (&v)[4][8]) {
             const int k0 = kc * KC;
-            float v[4][8];
-            if (a.a_mode == 0) {
-                const float* src = k0 < a.c1 ? a.x1 + rowc * a.ld1 + k0 : a.x2 + rowc * a.ld2 + (k0 - a.c1);
+            const float* src;
+            if (a.a_mode == 0) src = k0 < a.c1 ? a.x1 + c.rowc * a.ld1 + k0 : a.x2 + c.rowc * a.ld2 + (k0 - a.c1);
+            else src = a.G + c.srow * a.ldG + a.offG + k0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ldg8(src + q * 8, v[q]);
-            } else {
-                const float* gs = a.G + srow * a.ldG + a.offG + k0;
+            for (int q = 0; q < 4; ++q) ldg8(src + q * 8, v[q]);
+        };
+
+        if (wg < n_my) {
+            RowCtx cur, nxt;
+            int idx2;   // neighbour index two tiles (of this warpgroup) ahead
+            float v[4][8], vn[4][8];
+            nxt = make_ctx(wg, load_idx(wg));
+            idx2 = load_idx(wg + 2);
+            issue_loads(nxt, 0, vn);
+            for (int it = wg; it < n_my; it += 2) {
+                cur = nxt;
+                nxt = make_ctx(it + 2, idx2);       // positions of the next tile: in flight while this tile is processed
+                idx2 = load_idx(it + 4);
+                const float dx = cur.px - cur.qx, dy = cur.py - cur.qy, dz = cur.pz - cur.qz;
+                for (int kc = 0; kc < nk; ++kc) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ldg8(gs + q * 8, v[q]);
-                if (a.H != nullptr) {
-                    const float* hs = a.H + pt * a.ldH + a.offH + k0;
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[q][j] = vn[q][j];
+                    if (kc + 1 < nk) issue_loads(cur, kc + 1, vn);
+                    else if (it + 2 < n_my) issue_loads(nxt, 0, vn);
+                    const int k0 = kc * KC;
+                    if (a.a_mode == 1) {
+                        if (a.H != nullptr) {
+                            const float* hs = a.H + cur.pt * a.ldH + a.offH + k0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float h[8];
+                                ldg8(hs + q * 8, h);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[q][j] += h[j];
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float bb[8];
+                            lds8(sB1 + k0 + q * 8, bb);
+                            if (need_dir) {
+                                float w0[8], w1[8], w2[8];
+                                lds8(sWd1 + k0 + q * 8, w0);
+                                lds8(sWd1 + a.K + k0 + q * 8, w1);
+                                lds8(sWd1 + 2 * a.K + k0 + q * 8, w2);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[q][j] += dx * w0[j] + dy * w1[j] + dz * w2[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[q][j] = act_apply(v[q][j] + bb[j], a.act1);
+                        }
+                    }
+                    // each warpgroup owns two of the four A stages and waits on them strictly in order (an mbarrier
+                    // parity wait must never run more than one phase ahead of the barrier)
+                    const int j = (it >> 1) * nk + kc, as = wg * 2 + (j & 1);
+                    if (j >= 2) {
+                        ssf_mbar_wait(&a_empty[as], (uint32_t)(((j >> 1) - 1) & 1));
+                        tc_fence_after();
+                    }
+                    const uint32_t t_hi = tmem + lane_base + a_col0 + as * 64;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float h[8];
-                        ldg8(hs + q * 8, h);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[q][j] += h[j];
+                        float hi[8], lo[8];
+                        split8(v[q], hi, lo);
+                        tc_st8(t_hi + q * 8, hi);
+                        tc_st8(t_hi + 32 + q * 8, lo);
                     }
+                    tc_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&a_ready[as]);
                 }
-                if (a.Wd1 != nullptr) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float w0[8], w1[8], w2[8];
-                        ldg8(a.Wd1 + k0 + q * 8, w0);
-                        ldg8(a.Wd1 + a.K + k0 + q * 8, w1);
-                        ldg8(a.Wd1 + 2 * a.K + k0 + q * 8, w2);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[q][j] += dx * w0[j] + dy * w1[j] + dz * w2[j];
-                    }
-                }
-                if (a.b1 != nullptr) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float bb[8];
-                        ldg8(a.b1 + k0 + q * 8, bb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[q][j] += bb[j];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[q][j] = act_apply(v[q][j], a.act1);
             }
-            if (kc >= n_astage) {
-                ssf_mbar_wait(&a_empty[as], (uint32_t)((kc / n_astage - 1) & 1));
-                tc_fence_after();
-            }
-            const uint32_t t_hi = tmem + lane_base + a_col0 + as * 64;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float hi[8], lo[8];
-                split8(v[q], hi, lo);
-                tc_st8(t_hi + q * 8, hi);
-                tc_st8(t_hi + 32 + q * 8, lo);
-            }
-            tc_st_wait();
-            tc_fence_before();
-            mbar_arrive(&a_ready[as]);
         }
-        // ---- epilogue
-        ssf_mbar_wait(d_ready, 0);
-        tc_fence_after();
-        const int half = Nt >> 1;                      // columns per warpgroup (multiple of 8)
-        const int cbeg = wg * half, cend = cbeg + half;
-        const uint32_t t_d = tmem + lane_base;
-        float dot = 0.f;
-        for (int c = cbeg; c < cend; c += 8) {
-            float v[8];
-            tc_ld8(t_d + c, v);
-            tc_ld_wait();
-            const int cg = n0 + c;   // global output column
-            if (a.bias != nullptr) {
-                float bb[8];
-                ldg8(a.bias + cg, bb);
+    } else {
+        // ---- epilogue warps 8-11 (thread = row)
+        const int r = tid & 127;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const bool need_dir = a.Wd2 != nullptr;
+        for (int it = 0; it < n_my; ++it) {
+            const int db = it % cfg.nd;
+            const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r;
+            const bool valid = row < a.rows;
+            const long long rowc = valid ? row : a.rows - 1;
+            const long long pt = a.S > 0 ? rowc / a.S : 0;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (need_dir) {
+                const long long b = pt / a.Nq;
+                const float* ps = a.pos_src + (b * a.Nsrc + __ldg(a.idx + rowc)) * 3;
+                const float* pq = a.pos_q + pt * 3;
+                dx = __ldg(ps) - __ldg(pq);
+                dy = __ldg(ps + 1) - __ldg(pq + 1);
+                dz = __ldg(ps + 2) - __ldg(pq + 2);
+            }
+            ssf_mbar_wait(&d_full[db], (uint32_t)((it / cfg.nd) & 1));
+            tc_fence_after();
+            const uint32_t t_d = tmem + lane_base + (uint32_t)(db * Nt);
+            float dot = 0.f;
+            for (int c = 0; c < Nt; c += 8) {
+                float v[8], bb[8];
+                tc_ld8(t_d + c, v);
+                lds8(sBias + c, bb);
+                tc_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] += bb[j];
-            }
-            if (a.Hq != nullptr) {
-                float h[8];
-                ldg8(a.Hq + pt * a.ldHq + cg, h);
+                if (a.Hq != nullptr) {
+                    float h[8];
+                    ldg8(a.Hq + pt * a.ldHq + n0 + c, h);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += h[j];
-            }
-            if (a.Wd2 != nullptr) {
-                float w0[8], w1[8], w2[8];
-                ldg8(a.Wd2 + cg, w0);
-                ldg8(a.Wd2 + a.N + cg, w1);
-                ldg8(a.Wd2 + 2 * a.N + cg, w2);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += dx * w0[j] + dy * w1[j] + dz * w2[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
-            if (a.epi_mode == SSF_EPI_STORE) {
-                if (valid) {
-                    float* dst = a.y + row * a.ldy + cg;
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    for (int j = 0; j < 8; ++j) v[j] += h[j];
                 }
-            } else if (a.epi_mode == SSF_EPI_MAX) {
-                // rows beyond `rows` only exist in the last tile and belong to no stored point (rows % S == 0)
-                if (a.S == 16) {
-                    const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
-                    float w4[4], w2[2];
+                if (need_dir) {
+                    float w0[8], w1[8], w2[8];
+                    lds8(sWd2 + c, w0);
+                    lds8(sWd2 + Nt + c, w1);
+                    lds8(sWd2 + 2 * Nt + c, w2);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        w4[j] = fmaxf(u8 ? v[j + 4] : v[j], __shfl_xor_sync(0xffffffffu, u8 ? v[j] : v[j + 4], 8));
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        w2[j] = fmaxf(u4 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u4 ? w4[j] : w4[j + 2], 4));
-                    float w1 = fmaxf(u2 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, u2 ? w2[0] : w2[1], 2));
-                    w1 = fmaxf(w1, __shfl_xor_sync(0xffffffffu, w1, 1));
-                    if (valid && (lane & 1) == 0) a.y[pt * a.ldy + cg + ((lane >> 1) & 7)] = w1;
-                } else {  // S == 8
-                    const bool u4 = (lane & 4) != 0, u2 = (lane & 2) != 0, u1 = (lane & 1) != 0;
-                    float w4[4], w2[2];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        w4[j] = fmaxf(u4 ? v[j + 4] : v[j], __shfl_xor_sync(0xffffffffu, u4 ? v[j] : v[j + 4], 4));
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        w2[j] = fmaxf(u2 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u2 ? w4[j] : w4[j + 2], 2));
-                    const float w1 = fmaxf(u1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1));
-                    if (valid) a.y[pt * a.ldy + cg + (lane & 7)] = w1;
+                    for (int j = 0; j < 8; ++j) v[j] += dx * w0[j] + dy * w1[j] + dz * w2[j];
                 }
-            } else {  // DOT
-                float w[8];
-                ldg8(a.wvec + cg, w);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dot = fmaf(v[j], w[j], dot);
+                for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
+                const int cg = n0 + c;   // global output column
+                if (a.epi_mode == SSF_EPI_STORE) {
+                    if (valid) {
+                        float* dst = a.y + row * a.ldy + cg;
+                        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                } else if (a.epi_mode == SSF_EPI_MAX) {
+                    // rows beyond `rows` only exist in the last tile and belong to no stored point (rows % S == 0)
+                    if (a.S == 16) {
+                        const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
+                        float w4[4], w2[2];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            w4[j] = fmaxf(u8 ? v[j + 4] : v[j], __shfl_xor_sync(0xffffffffu, u8 ? v[j] : v[j + 4], 8));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            w2[j] = fmaxf(u4 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u4 ? w4[j] : w4[j + 2], 4));
+                        float w1 = fmaxf(u2 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, u2 ? w2[0] : w2[1], 2));
+                        w1 = fmaxf(w1, __shfl_xor_sync(0xffffffffu, w1, 1));
+                        if (valid && (lane & 1) == 0) a.y[pt * a.ldy + cg + ((lane >> 1) & 7)] = w1;
+                    } else {  // S == 8
+                        const bool u4 = (lane & 4) != 0, u2 = (lane & 2) != 0, u1 = (lane & 1) != 0;
+                        float w4[4], w2[2];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            w4[j] = fmaxf(u4 ? v[j + 4] : v[j], __shfl_xor_sync(0xffffffffu, u4 ? v[j] : v[j + 4], 4));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            w2[j] = fmaxf(u2 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u2 ? w4[j] : w4[j + 2], 2));
+                        const float w1 = fmaxf(u1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1));
+                        if (valid) a.y[pt * a.ldy + cg + (lane & 7)] = w1;
+                    }
+                } else {  // DOT
+                    float w[8];
+                    lds8(sWvec + c, w);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dot = fmaf(v[j], w[j], dot);
+                }
             }
-        }
-        if (a.epi_mode == SSF_EPI_DOT) {
-            float* sDot = reinterpret_cast<float*>(tmem_slot + 4);   // [128]
-            if (wg == 1) sDot[r] = dot;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (wg == 0 && valid) a.y[row] = dot + sDot[r] + a.b0;
+            tc_fence_before();
+            mbar_arrive(&d_empty[db]);
+            if (a.epi_mode == SSF_EPI_DOT && valid) a.y[row] = dot + a.b0;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc_dealloc(tmem, (uint32_t)tmem_cols);
+    if (warp == 12) tc_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -299,7 +401,7 @@ extern "C" int ssf_dense_args_bytes(void) { return (int)sizeof(ssf_dense_args); 
 extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     ssf_dense_args a = *args;
     if (a.rows <= 0) return ssf_arg_error("dense_tc: empty input");
-    if (a.K <= 0 || a.K % KC) return ssf_arg_error("dense_tc: K must be a positive multiple of 32");
+    if (a.K <= 0 || a.K % KC || a.K > 512) return ssf_arg_error("dense_tc: K must be a positive multiple of 32, <= 512");
     if (a.N < 32 || a.N % 32 || (a.N > 256 && a.N % 256)) return ssf_arg_error("dense_tc: N must be a multiple of 32 (of 256 above 256)");
     if (a.a_mode == 0) {
         if (a.x1 == nullptr || a.c1 % KC || (a.x2 != nullptr && a.c2 % KC) || a.c1 + (a.x2 ? a.c2 : 0) != a.K)
@@ -313,18 +415,25 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     if (a.epi_mode == SSF_EPI_DOT && (a.N > 256 || a.wvec == nullptr)) return ssf_arg_error("dense_tc: dot epilogue needs N <= 256 and wvec");
     if ((a.Wd1 != nullptr || a.Wd2 != nullptr) && (a.pos_src == nullptr || a.pos_q == nullptr || a.idx == nullptr))
         return ssf_arg_error("dense_tc: direction term needs pos_src, pos_q, idx");
-    const int Nt = a.N < 256 ? a.N : 256;
-    const int tmem_cols = Nt <= 128 ? 256 : 512;
-    const int n_astage = Nt <= 128 ? 2 : 4;
-    const size_t smem = (size_t)WSTAGES * Nt * KC * 4 * 2 + 32 * 8 + 128 * 4;
+    DenseCfg cfg;
+    cfg.Nt = a.N < 256 ? a.N : 256;
+    cfg.nk = a.K / KC;
+    const size_t wchunk = (size_t)cfg.Nt * KC * 4 * 2;
+    cfg.resident = (size_t)cfg.nk * wchunk <= (size_t)W_SMEM_MAX;
+    cfg.nstage = cfg.resident ? cfg.nk : (int)(W_SMEM_MAX / wchunk);
+    if (cfg.nstage > 16) cfg.nstage = 16;
+    cfg.nd = (2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1;
+    cfg.n_tiles = (int)((a.rows + 127) / 128);
+    const size_t smem = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return ssf_set_error(e);
         attr_set = true;
     }
-    dim3 grid((unsigned)((a.rows + 127) / 128), (unsigned)((a.N + 255) / 256));
-    dense_tc_kernel<<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, n_astage, tmem_cols);
+    int n_sm = 148;
+    dim3 grid((unsigned)(cfg.n_tiles < n_sm ? cfg.n_tiles : n_sm), (unsigned)((a.N + 255) / 256));
+    dense_tc_kernel<<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

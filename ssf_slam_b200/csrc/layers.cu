@@ -259,7 +259,8 @@ extern "C" int ssf_transpose(const float* in, int B, int R, int C, float* out, v
 // query [B,N,3], src_pos [B,M,3], src_val [B,M,C], idx [B,N,k] -> out [B,N,C]; k <= 16
 __global__ void __launch_bounds__(128)
 interpolate_kernel(const float* __restrict__ query, const float* __restrict__ src_pos, const float* __restrict__ src_val,
-                   const int* __restrict__ idx, int N, int M, int C, int k, int mode, float clampv, float* __restrict__ out) {
+                   const int* __restrict__ idx, int ld_idx, int N, int M, int C, int k, int mode, float clampv,
+                   float* __restrict__ out) {
     const int b = blockIdx.y;
     const int n = blockIdx.x * 4 + (threadIdx.x >> 5);  // one warp per query point
     const int lane = threadIdx.x & 31;
@@ -269,7 +270,7 @@ interpolate_kernel(const float* __restrict__ query, const float* __restrict__ sr
     float inv = 0.f;
     int id = 0;
     if (lane < k) {
-        id = idx[((size_t)b * N + n) * k + lane];
+        id = idx[((size_t)b * N + n) * ld_idx + lane];
         const float* s = src_pos + ((size_t)b * M + id) * 3;
         const float dx = s[0] - qx, dy = s[1] - qy, dz = s[2] - qz;
         const float d = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-10f);
@@ -293,13 +294,13 @@ interpolate_kernel(const float* __restrict__ query, const float* __restrict__ sr
     }
 }
 
-extern "C" int ssf_interpolate(const float* query, const float* src_pos, const float* src_val, const int* idx, int B, int N,
-                               int M, int C, int k, int mode, float clampv, float* out, void* stream) {
+extern "C" int ssf_interpolate(const float* query, const float* src_pos, const float* src_val, const int* idx, int ld_idx, int B,
+                               int N, int M, int C, int k, int mode, float clampv, float* out, void* stream) {
     if (B <= 0 || N <= 0 || C <= 0) return ssf_arg_error("interpolate: empty input");
-    if (k <= 0 || k > 16) return ssf_arg_error("interpolate: k must be in [1,16]");
+    if (k <= 0 || k > 16 || ld_idx < k) return ssf_arg_error("interpolate: k must be in [1,16] and ld_idx >= k");
     if (mode == 1 && C != 3) return ssf_arg_error("interpolate: warp mode needs C == 3");
     dim3 grid((N + 3) / 4, B);
-    interpolate_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, N, M, C, k, mode, clampv, out);
+    interpolate_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, mode, clampv, out);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

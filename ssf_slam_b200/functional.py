@@ -173,12 +173,14 @@ def knn_idx(k, query, ref, offset=None):
     return idx
 
 
-def interpolate(query, src_pos, src_val, idx, mode=0, clampv=100.0):
+def interpolate(query, src_pos, src_val, idx, mode=0, clampv=100.0, k=None):
+    """idx i32 [B,N,kk] with kk >= k: the first k entries of every row are used (default k = kk)."""
     B, N, _ = query.shape
     M, C = src_val.shape[1], src_val.shape[2]
-    k = idx.shape[2]
+    ld = idx.shape[2]
+    k = ld if k is None else k
     out = torch.empty(B, N, C, dtype=torch.float32, device=query.device)
-    nat.check(nat.lib().ssf_interpolate(nat.ptr(query), nat.ptr(src_pos), nat.ptr(src_val), nat.ptr(idx), B, N, M, C, k,
+    nat.check(nat.lib().ssf_interpolate(nat.ptr(query), nat.ptr(src_pos), nat.ptr(src_val), nat.ptr(idx), ld, B, N, M, C, k,
                                         mode, float(clampv), nat.ptr(out), nat.stream()))
     return out
 

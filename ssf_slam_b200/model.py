@@ -259,9 +259,14 @@ def set_abstraction_pm(w, npoint, nsample, xyz, feats):
     return new_xyz, out, fps_idx
 
 
-def set_upconv_pm(w, nsample, pos1, pos2, feat1, feat2):
+def set_upconv_pm(w, nsample, pos1, pos2, feat1, feat2, return_idx=False):
     """Feature propagation sparse (pos2, feat2) -> dense (pos1, feat1): [B,N1,mlp2[-1]]."""
     idx = F_.knn_idx(nsample, pos1, pos2)
+    out = _set_upconv_body(w, idx, pos1, pos2, feat1, feat2)
+    return (out, idx) if return_idx else out
+
+
+def _set_upconv_body(w, idx, pos1, pos2, feat1, feat2):
     if _tc():
         G = F_.dense_tc(w["Wg_img"], w["C1"], feat2.shape[-1], x1=feat2)
         pooled = F_.dense_tc(w["W2_img"], w["C2"], w["C1"], G=G, b1=w["b1"], Wd1=w["Wd"], act1=ACT_RELU, idx=idx, pos_src=pos2,
@@ -274,10 +279,12 @@ def set_upconv_pm(w, nsample, pos1, pos2, feat1, feat2):
     return F_.linear(x, w["M2"], w["MC2"], bias=w["mb2"], act=ACT_RELU)
 
 
-def upsample_pm(xyz, sparse_xyz, sparse_val, k=3):
-    """UpsampleFlow: [B,S,C] on sparse_xyz -> [B,N,C] on xyz."""
-    idx = F_.knn_idx(k, xyz, sparse_xyz)
-    return F_.interpolate(xyz, sparse_xyz, sparse_val, idx, mode=0, clampv=100.0)
+def upsample_pm(xyz, sparse_xyz, sparse_val, k=3, idx=None):
+    """UpsampleFlow: [B,S,C] on sparse_xyz -> [B,N,C] on xyz.  `idx` may be any (distance, index)-ordered neighbour list
+    of xyz in sparse_xyz with at least k entries per row (its k-prefix IS the k-NN list the reference computes)."""
+    if idx is None:
+        idx = F_.knn_idx(k, xyz, sparse_xyz)
+    return F_.interpolate(xyz, sparse_xyz, sparse_val, idx, mode=0, clampv=100.0, k=k)
 
 
 def point_warping_pm(pos1, pos2, flow1, k):
@@ -428,18 +435,21 @@ class TFlow(nn.Module):
         flows = [flow]
         for lvl, su, fr, dc, k_up, k_warp in ((2, "su2", "flow2_r", "deconv3_2", 5, 5), (1, "su1", "flow1_r", "deconv2_1", 5, 7),
                                              (0, "su0", "flow0_r", "deconv1_0", 7, 7)):
-            up = set_upconv_pm(W[su], 16, xyz[lvl], xyz[lvl + 1], feats[lvl], up)
+            # the 16-NN lists of the up-conv (dense level in sparse level, both clouds) also serve the four UpsampleFlow
+            # calls of cloud 1: their k = 5/7 and k = 3 lists are prefixes (ASF/utils/soflow.py:1459-1461)
+            up, idx_up = set_upconv_pm(W[su], 16, xyz[lvl], xyz[lvl + 1], feats[lvl], up, return_idx=True)
+            idx_up = idx_up[:B]
             p1, p1s = h1(xyz[lvl]), h1(xyz[lvl + 1])
             p2 = h2(xyz[lvl])
-            coarse = upsample_pm(p1, p1s, flow, k_up)
-            sf_feat = upsample_pm(p1, p1s, ff, k_up)
+            coarse = upsample_pm(p1, p1s, flow, k_up, idx=idx_up)
+            sf_feat = upsample_pm(p1, p1s, ff, k_up, idx=idx_up)
             dcin, dcout = W[dc].shape
             if _tc():
-                cfu = F_.dense_tc(W[dc + "_img"], dcout, dcin, x1=upsample_pm(p1, p1s, cf, 3), act=ACT_LEAKY)
-                cbu = F_.dense_tc(W[dc + "_img"], dcout, dcin, x1=upsample_pm(p1, p1s, cb, 3), act=ACT_LEAKY)
+                cfu = F_.dense_tc(W[dc + "_img"], dcout, dcin, x1=upsample_pm(p1, p1s, cf, 3, idx=idx_up), act=ACT_LEAKY)
+                cbu = F_.dense_tc(W[dc + "_img"], dcout, dcin, x1=upsample_pm(p1, p1s, cb, 3, idx=idx_up), act=ACT_LEAKY)
             else:
-                cfu = F_.linear(upsample_pm(p1, p1s, cf, 3), W[dc], dcout, act=ACT_LEAKY)
-                cbu = F_.linear(upsample_pm(p1, p1s, cb, 3), W[dc], dcout, act=ACT_LEAKY)
+                cfu = F_.linear(upsample_pm(p1, p1s, cf, 3, idx=idx_up), W[dc], dcout, act=ACT_LEAKY)
+                cbu = F_.linear(upsample_pm(p1, p1s, cb, 3, idx=idx_up), W[dc], dcout, act=ACT_LEAKY)
             warped = point_warping_pm(p1, p2, coarse, k_warp)
             cf, cb, ff, flow = cost_volume_pm(W[fr], p1, p2, warped, h1(up), cfu, h2(up), cbu, sf=coarse, sf_feat=sf_feat)
             flows.append(flow)

@@ -98,7 +98,11 @@ def _act(x, act):
 
 
 @pytest.mark.parametrize("rows,K,N,two_seg,act", [(128, 32, 32, False, 0), (1000, 96, 128, True, 2), (4096, 256, 256, False, 1),
-                                                  (300, 512, 256, True, 1), (2048, 256, 512, False, 1), (257, 64, 64, False, 2)])
+                                                  (300, 512, 256, True, 1), (2048, 256, 512, False, 1), (257, 64, 64, False, 2),
+                                                  # many tiles per persistent CTA: barrier phase bookkeeping, both producer warpgroups
+                                                  (148 * 128 * 5 + 77, 64, 64, False, 2), (148 * 128 * 3, 32, 32, False, 1),
+                                                  (148 * 128 * 4 + 1, 256, 256, False, 1), (148 * 128 * 3 + 130, 96, 128, True, 0),
+                                                  (148 * 128 * 2 + 5, 256, 128, False, 2)])
 def test_dense_tc_rows(rows, K, N, two_seg, act):
     from ssf_slam_b200 import functional as F_, tc
     g = torch.Generator().manual_seed(rows + K + N)
@@ -118,7 +122,7 @@ def test_dense_tc_rows(rows, K, N, two_seg, act):
 
 
 @pytest.mark.parametrize("B,Nsrc,Nq,S,K,N,epi", [(2, 300, 100, 16, 64, 64, 0), (3, 200, 72, 8, 256, 512, 1), (2, 500, 333, 16, 128, 128, 1),
-                                                  (2, 128, 64, 16, 128, 64, 2)])
+                                                  (2, 128, 64, 16, 128, 64, 2), (3, 2048, 4000, 16, 64, 64, 1), (2, 512, 5000, 8, 32, 64, 0)])
 def test_dense_tc_grouped(B, Nsrc, Nq, S, K, N, epi):
     """Grouped first layer on the fly (gather + per-point block + direction term), per-point epilogue add, max / dot."""
     from ssf_slam_b200 import functional as F_, tc

@@ -28,7 +28,8 @@ namespace {
 constexpr int KC = 32;                    // K chunk
 constexpr int AS = 4;                     // TMEM A stages (64 columns each: hi | lo)
 constexpr int DT_THREADS = 448;
-constexpr int W_SMEM_MAX = 192 * 1024;    // bytes of shared memory for weight images
+constexpr int W_SMEM_MAX = 160 * 1024;    // bytes of shared memory for weight images
+constexpr int STG_LD = KC + 4;            // row stride (floats) of a producer warp's transpose tile
 
 struct DenseCfg {
     int Nt;          // columns of a CTA tile
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
     uint64_t* d_full = bars + 40;                   // [2]
     uint64_t* d_empty = bars + 42;                  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
+    float* sStage = reinterpret_cast<float*>(bars + 46);   // [8 producer warps][32 rows][STG_LD]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 12) tc_alloc(tmem_slot, 512);
@@ -220,19 +222,42 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
             }
             return c;
         };
-        auto issue_loads = [&](const RowCtx& c, int kc, float (&v)[4][8]) {
+        // Coalesced loads: 8 lanes x 16 bytes cover the 128-byte K chunk of one row, 4 rows per instruction (a thread
+        // reading its own row would touch 32 different lines per instruction).  Lane l therefore fetches pieces of rows
+        // 4 j + (l >> 3); the chunk is transposed back to thread = row through this warp's shared-memory tile.
+        const int rg = lane >> 3, pc = lane & 7;
+        float* stg = sStage + warp * (32 * STG_LD);
+        auto issue_loads = [&](const RowCtx& c, int kc, float4 (&v)[8]) {
             const int k0 = kc * KC;
-            const float* src;
-            if (a.a_mode == 0) src = k0 < a.c1 ? a.x1 + c.rowc * a.ld1 + k0 : a.x2 + c.rowc * a.ld2 + (k0 - a.c1);
-            else src = a.G + c.srow * a.ldG + a.offG + k0;
+            const int my = a.a_mode == 0 ? (int)c.rowc : (int)c.srow;   // row index in the source array (fits 31 bits)
+            const float* base;
+            long long ld;
+            if (a.a_mode == 0) {
+                if (k0 < a.c1) { base = a.x1 + k0; ld = a.ld1; } else { base = a.x2 + (k0 - a.c1); ld = a.ld2; }
+            } else {
+                base = a.G + a.offG + k0;
+                ld = a.ldG;
+            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ldg8(src + q * 8, v[q]);
+            for (int j = 0; j < 8; ++j) {
+                const int rrow = __shfl_sync(0xffffffffu, my, j * 4 + rg);
+                v[j] = __ldg(reinterpret_cast<const float4*>(base + (long long)rrow * ld + pc * 4));
+            }
+        };
+        auto transpose_in = [&](const float4 (&vin)[8], float (&v)[4][8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + (j * 4 + rg) * STG_LD + pc * 4) = vin[j];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) lds8(stg + lane * STG_LD + q * 8, v[q]);
+            __syncwarp();
         };
 
         if (wg < n_my) {
             RowCtx cur, nxt;
             int idx2;   // neighbour index two tiles (of this warpgroup) ahead
-            float v[4][8], vn[4][8];
+            float v[4][8];
+            float4 vn[8];
             nxt = make_ctx(wg, load_idx(wg));
             idx2 = load_idx(wg + 2);
             issue_loads(nxt, 0, vn);
@@ -242,10 +267,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
                 idx2 = load_idx(it + 4);
                 const float dx = cur.px - cur.qx, dy = cur.py - cur.qy, dz = cur.pz - cur.qz;
                 for (int kc = 0; kc < nk; ++kc) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[q][j] = vn[q][j];
+                    transpose_in(vn, v);
                     if (kc + 1 < nk) issue_loads(cur, kc + 1, vn);
                     else if (it + 2 < n_my) issue_loads(nxt, 0, vn);
                     const int k0 = kc * KC;
@@ -321,67 +343,79 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
             tc_fence_after();
             const uint32_t t_d = tmem + lane_base + (uint32_t)(db * Nt);
             float dot = 0.f;
-            for (int c = 0; c < Nt; c += 8) {
-                float v[8], bb[8];
-                tc_ld8(t_d + c, v);
-                lds8(sBias + c, bb);
+            for (int c = 0; c < Nt; c += 16) {
+                float v[16];
+                tc_ld16(t_d + c, v);
                 tc_ld_wait();
+                const int cg = n0 + c;   // global output column
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += bb[j];
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sBias + c + q * 4);
+                    v[q * 4] += bb.x; v[q * 4 + 1] += bb.y; v[q * 4 + 2] += bb.z; v[q * 4 + 3] += bb.w;
+                }
                 if (a.Hq != nullptr) {
-                    float h[8];
-                    ldg8(a.Hq + pt * a.ldHq + n0 + c, h);
+                    const float4* h4 = reinterpret_cast<const float4*>(a.Hq + pt * a.ldHq + cg);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += h[j];
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 h = __ldg(h4 + q);
+                        v[q * 4] += h.x; v[q * 4 + 1] += h.y; v[q * 4 + 2] += h.z; v[q * 4 + 3] += h.w;
+                    }
                 }
                 if (need_dir) {
-                    float w0[8], w1[8], w2[8];
-                    lds8(sWd2 + c, w0);
-                    lds8(sWd2 + Nt + c, w1);
-                    lds8(sWd2 + 2 * Nt + c, w2);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += dx * w0[j] + dy * w1[j] + dz * w2[j];
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(sWd2 + c + q * 4);
+                        const float4 w1 = *reinterpret_cast<const float4*>(sWd2 + Nt + c + q * 4);
+                        const float4 w2 = *reinterpret_cast<const float4*>(sWd2 + 2 * Nt + c + q * 4);
+                        v[q * 4] += dx * w0.x + dy * w1.x + dz * w2.x;
+                        v[q * 4 + 1] += dx * w0.y + dy * w1.y + dz * w2.y;
+                        v[q * 4 + 2] += dx * w0.z + dy * w1.z + dz * w2.z;
+                        v[q * 4 + 3] += dx * w0.w + dy * w1.w + dz * w2.w;
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
-                const int cg = n0 + c;   // global output column
+                for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], a.act);
                 if (a.epi_mode == SSF_EPI_STORE) {
                     if (valid) {
                         float* dst = a.y + row * a.ldy + cg;
-                        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                     }
                 } else if (a.epi_mode == SSF_EPI_MAX) {
-                    // rows beyond `rows` only exist in the last tile and belong to no stored point (rows % S == 0)
-                    if (a.S == 16) {
-                        const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
-                        float w4[4], w2[2];
+                    // butterfly max over the S rows (= lanes) of a point; rows beyond `rows` only exist in the last tile
+                    // and belong to no stored point (rows % S == 0)
+                    if (a.S == 16) {   // 16 values over 16 lanes: lane s ends up with column c + s
+                        const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0, u1 = (lane & 1) != 0;
+                        float w8[8], w4[4], w2[2];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            w4[j] = fmaxf(u8 ? v[j + 4] : v[j], __shfl_xor_sync(0xffffffffu, u8 ? v[j] : v[j + 4], 8));
+                        for (int j = 0; j < 8; ++j) w8[j] = fmaxf(u8 ? v[j + 8] : v[j], __shfl_xor_sync(0xffffffffu, u8 ? v[j] : v[j + 8], 8));
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                            w2[j] = fmaxf(u4 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u4 ? w4[j] : w4[j + 2], 4));
-                        float w1 = fmaxf(u2 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, u2 ? w2[0] : w2[1], 2));
-                        w1 = fmaxf(w1, __shfl_xor_sync(0xffffffffu, w1, 1));
-                        if (valid && (lane & 1) == 0) a.y[pt * a.ldy + cg + ((lane >> 1) & 7)] = w1;
-                    } else {  // S == 8
-                        const bool u4 = (lane & 4) != 0, u2 = (lane & 2) != 0, u1 = (lane & 1) != 0;
-                        float w4[4], w2[2];
+                        for (int j = 0; j < 4; ++j) w4[j] = fmaxf(u4 ? w8[j + 4] : w8[j], __shfl_xor_sync(0xffffffffu, u4 ? w8[j] : w8[j + 4], 4));
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            w4[j] = fmaxf(u4 ? v[j + 4] : v[j], __shfl_xor_sync(0xffffffffu, u4 ? v[j] : v[j + 4], 4));
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                            w2[j] = fmaxf(u2 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u2 ? w4[j] : w4[j + 2], 2));
+                        for (int j = 0; j < 2; ++j) w2[j] = fmaxf(u2 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u2 ? w4[j] : w4[j + 2], 2));
                         const float w1 = fmaxf(u1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1));
-                        if (valid) a.y[pt * a.ldy + cg + (lane & 7)] = w1;
+                        if (valid) a.y[pt * a.ldy + cg + (lane & 15)] = w1;
+                    } else {           // S == 8: 16 values over 8 lanes: lane s ends up with columns c + 2 s, c + 2 s + 1
+                        const bool u4 = (lane & 4) != 0, u2 = (lane & 2) != 0, u1 = (lane & 1) != 0;
+                        float w8[8], w4[4], w2[2];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w8[j] = fmaxf(u4 ? v[j + 8] : v[j], __shfl_xor_sync(0xffffffffu, u4 ? v[j] : v[j + 8], 4));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) w4[j] = fmaxf(u2 ? w8[j + 4] : w8[j], __shfl_xor_sync(0xffffffffu, u2 ? w8[j] : w8[j + 4], 2));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) w2[j] = fmaxf(u1 ? w4[j + 2] : w4[j], __shfl_xor_sync(0xffffffffu, u1 ? w4[j] : w4[j + 2], 1));
+                        if (valid) *reinterpret_cast<float2*>(a.y + pt * a.ldy + cg + 2 * (lane & 7)) = make_float2(w2[0], w2[1]);
                     }
                 } else {  // DOT
-                    float w[8];
-                    lds8(sWvec + c, w);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dot = fmaf(v[j], w[j], dot);
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w = *reinterpret_cast<const float4*>(sWvec + c + q * 4);
+                        dot = fmaf(v[q * 4], w.x, dot);
+                        dot = fmaf(v[q * 4 + 1], w.y, dot);
+                        dot = fmaf(v[q * 4 + 2], w.z, dot);
+                        dot = fmaf(v[q * 4 + 3], w.w, dot);
+                    }
                 }
             }
             tc_fence_before();
@@ -424,7 +458,7 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     if (cfg.nstage > 16) cfg.nstage = 16;
     cfg.nd = (2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1;
     cfg.n_tiles = (int)((a.rows + 127) / 128);
-    const size_t smem = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
+    const size_t smem = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8 + (size_t)8 * 32 * STG_LD * 4;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

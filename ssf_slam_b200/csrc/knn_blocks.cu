@@ -4,10 +4,11 @@
 //
 // build : one CTA per reference cloud sorts the points along a 30-bit Morton curve (bitonic sort in shared memory),
 //         stores them as float4 (x, y, z, original index) and the bounding box of every block of 32 consecutive points.
-// search: one warp per query.  Lane l owns the lower bounds lb(q, box) of blocks l, l+32, ...; the warp repeatedly
-//         picks the unvisited block with the smallest bound, evaluates its 32 points in parallel (lane = point, one
-//         coalesced 512-byte load) and merges the survivors into a lane-distributed sorted list (lane j = j-th best).
-//         It stops when the smallest remaining bound exceeds the current k-th distance.
+// search: one warp per query.  Lane l owns the lower bounds lb(q, box) of blocks l, l+32, ...  The nearest block's 32
+//         points (lane = point, one coalesced 512-byte load) are sorted across the lanes by a bitonic network and become
+//         the candidate list (lane j = j-th best); a few more nearest-first visits tighten the k-th distance, then every
+//         remaining block whose bound does not exceed it is visited in index order (re-tested as the bound shrinks).
+//         Survivors of a visited block are merged into the lane-distributed list with ballot / shuffle-up inserts.
 // Exactness: every box bound is computed with the SAME rounded operations as the point distance and each of them
 // (fsub, fmul, fadd) is monotone, so bound <= distance of every point inside the box holds in floating point, not
 // just in exact arithmetic; blocks are skipped only on bound > kth (strict), so index ties are never lost.
@@ -173,30 +174,9 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
         }
         float list_d = CUDART_INF_F, kth_d = CUDART_INF_F;
         int list_i = 0x7fffffff, kth_i = 0x7fffffff;
-        while (true) {
-            float best = lb[0];
-            int bs = 0;
-#pragma unroll
-            for (int s = 1; s < NBL; ++s)
-                if (lb[s] < best) {
-                    best = lb[s];
-                    bs = s;
-                }
-            int bblk = bs * 32 + lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bblk, o);
-                if (ob < best || (ob == best && ok < bblk)) {
-                    best = ob;
-                    bblk = ok;
-                }
-            }
-            if (best == CUDART_INF_F || best > kth_d) break;   // nothing left, or no remaining box can hold a better point
-#pragma unroll
-            for (int s = 0; s < NBL; ++s)
-                if (s == (bblk >> 5) && lane == (bblk & 31)) lb[s] = CUDART_INF_F;
-            const float4 p = __ldg(P + (size_t)bblk * 32 + lane);
+        // evaluates block `blk` (lane = point) and merges the survivors into the lane-distributed sorted list
+        auto visit = [&](int blk) {
+            const float4 p = __ldg(P + (size_t)blk * 32 + lane);
             const float d = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z);
             const int pi = __float_as_int(p.w);
             unsigned mask = __ballot_sync(0xffffffffu, key_less(d, pi, kth_d, kth_i));
@@ -218,6 +198,85 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
                 }
                 kth_d = __shfl_sync(0xffffffffu, list_d, k - 1);
                 kth_i = __shfl_sync(0xffffffffu, list_i, k - 1);
+            }
+        };
+        // warp-wide argmin of the remaining bounds; marks the winner visited.  Returns -1 when nothing is left.
+        auto pop_nearest = [&](float& best_out) -> int {
+            float best = lb[0];
+            int bs = 0;
+#pragma unroll
+            for (int s = 1; s < NBL; ++s)
+                if (lb[s] < best) {
+                    best = lb[s];
+                    bs = s;
+                }
+            int bblk = bs * 32 + lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bblk, o);
+                if (ob < best || (ob == best && ok < bblk)) {
+                    best = ob;
+                    bblk = ok;
+                }
+            }
+            best_out = best;
+            if (best == CUDART_INF_F) return -1;
+#pragma unroll
+            for (int s = 0; s < NBL; ++s)
+                if (s == (bblk >> 5) && lane == (bblk & 31)) lb[s] = CUDART_INF_F;
+            return bblk;
+        };
+        // 1) seed: the nearest block's 32 points, sorted across the lanes by a bitonic network, become the list
+        {
+            float best;
+            const int blk = pop_nearest(best);   // >= 0: there is at least one block
+            const float4 p = __ldg(P + (size_t)blk * 32 + lane);
+            float d = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z);
+            int pi = __float_as_int(p.w);
+#pragma unroll
+            for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, d, j);
+                    const int oi = __shfl_xor_sync(0xffffffffu, pi, j);
+                    const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                    if (take_min == key_less(od, oi, d, pi)) {
+                        d = od;
+                        pi = oi;
+                    }
+                }
+            }
+            list_d = d;
+            list_i = pi;
+            kth_d = __shfl_sync(0xffffffffu, list_d, k - 1);
+            kth_i = __shfl_sync(0xffffffffu, list_i, k - 1);
+        }
+        // 2) a few nearest-first visits tighten the k-th distance quickly
+#pragma unroll 1
+        for (int rep = 0; rep < 3; ++rep) {
+            float best;
+            const int blk = pop_nearest(best);
+            if (blk < 0 || best > kth_d) {   // nothing left, or no remaining box can hold a better point
+                if (blk >= 0) {              // (put the popped block back: the sweep below re-tests it)
+#pragma unroll
+                    for (int s = 0; s < NBL; ++s)
+                        if (s == (blk >> 5) && lane == (blk & 31)) lb[s] = best;
+                }
+                break;
+            }
+            visit(blk);
+        }
+        // 3) sweep: every remaining block whose bound does not exceed the (shrinking) k-th distance, in index order
+#pragma unroll
+        for (int s = 0; s < NBL; ++s) {
+            unsigned m = __ballot_sync(0xffffffffu, lb[s] <= kth_d && lb[s] != CUDART_INF_F);
+            while (m) {
+                const int bl = __ffs(m) - 1;
+                m &= m - 1;
+                const float blb = __shfl_sync(0xffffffffu, lb[s], bl);
+                if (blb > kth_d) continue;   // warp-uniform
+                visit(s * 32 + bl);
             }
         }
         if (lane < k) {

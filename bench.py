@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="frame pairs per step per GPU")
     ap.add_argument("--npoints", type=int, default=8192)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -146,6 +146,63 @@ def cost_volume_flops(n1, m):
     return 2.0 * n1 * per_point
 
 
+def point_op_rooflines(B, N, dev):
+    """Stand-alone pointnet2 operators (the B-op boundary, reference layouts) on B clouds of N points: achieved HBM GB/s =
+    ALGORITHMIC bytes / CUDA-event time for the gathers, work rates for FPS / kNN / ball query (not HBM
+    bound).  Inputs are larger than L2 in aggregate or freshly produced; 3 warm-ups, 5 timed launches each."""
+    import torch
+    from ssf_slam_b200 import pointnet2_utils as pu
+    pk = peaks()
+    g = torch.Generator(device=dev).manual_seed(0)
+    xyz = torch.randn(B, N, 3, device=dev, generator=g) * torch.tensor([30.0, 20.0, 2.0], device=dev)
+    M = 2048
+    fps_idx = pu.furthest_point_sample(xyz, M)
+    new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2).contiguous()
+    _, idx16 = pu.knn(16, xyz, xyz)
+    feat96 = torch.randn(B, 96, N, device=dev, generator=g)
+    w3 = torch.rand(B, N, 3, device=dev, generator=g)
+    idx3 = idx16[:, :, :3].contiguous()
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    out = []
+
+    def hbm(name, byts, dram, fn):
+        """byts = algorithmic bytes (gathered reads counted as memory reads); dram = compulsory DRAM bytes
+        (unique source + indices + output): the gathers hit shared memory / L2, so `frac` can exceed 1 while
+        `dram_frac` <= 1 is the fraction of the HBM roofline the compulsory stream reaches."""
+        t = timed(fn)
+        out.append({"op": name, "bound": "hbm", "achieved": byts / t / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": byts / t / 1e9 / pk["hbm"], "dram_achieved": dram / t / 1e9, "dram_frac": dram / t / 1e9 / pk["hbm"],
+                    "ms": t * 1e3})
+
+    def rate(name, work, unit, fn):
+        t = timed(fn)
+        out.append({"op": name, "bound": "alu/latency", "achieved": work / t / 1e9, "unit": unit, "ms": t * 1e3})
+
+    C, S = 96, 16
+    hbm("grouping_operation[C=96,M=%d,S=16]" % N, B * (4.0 * N * S + 8.0 * C * N * S), B * (4.0 * N * S + 4.0 * C * N + 4.0 * C * N * S),
+        lambda: pu.grouping_operation(feat96, idx16))
+    hbm("three_interpolate[C=96,n=%d]" % N, B * (4.0 * 3 * N * 2 + 4.0 * C * N * 3 + 4.0 * C * N), B * (4.0 * 3 * N * 2 + 8.0 * C * N),
+        lambda: pu.three_interpolate(feat96, idx3, w3))
+    hbm("gather_operation[C=96,M=%d]" % M, B * (4.0 * M + 8.0 * C * M), B * (4.0 * M + 4.0 * C * N + 4.0 * C * M),
+        lambda: pu.gather_operation(feat96, fps_idx))
+    rate("furthest_point_sample[N=%d,n=%d]" % (N, M), B * float(N) * M, "G point-updates/s", lambda: pu.furthest_point_sample(xyz, M))
+    rate("knn[k=16,%dx%d]" % (N, N), B * float(N) * N, "G pair-evaluations/s (brute-force equivalent)", lambda: pu.knn(16, xyz, xyz))
+    rate("ball_query[r=1.0,ns=16,%dx%d]" % (M, N), B * float(N) * M, "G pair-evaluations/s", lambda: pu.ball_query(1.0, 16, xyz, new_xyz))
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +309,8 @@ def main():
     prof.disable()
     keep.clear()
 
+    point_ops = point_op_rooflines(B, N, dev) if rank == 0 else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -273,7 +332,9 @@ def main():
             ach = B * cost_volume_flops(dims["N1"], dims["m"]) / avg_s / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
                     "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["source"],
-                    "note": "fp32 FFMA realisation (fp32-parity path); algorithmic 2*MAC of one launch over B clouds / its mean duration"}
+                    "note": ("tcgen05 kind::tf32 with the fp32-faithful 3xTF32 split (3 MMA passes per algorithmic MAC) for m=64, "
+                             "CUDA-core S x S attention inside the same kernel; achieved = algorithmic 2*MAC of one launch over "
+                             "B clouds / its mean CUDA-event duration; peak = measured dense bf16 cuBLAS throughput")}
         elif top.startswith("knn"):
             byts = B * (12.0 * (dims["Nq"] + dims["Nr"]) + 4.0 * dims["Nq"] * dims["k"])
             roof = {"kernel": top, "bound": "hbm", "achieved": byts / avg_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
@@ -296,7 +357,7 @@ def main():
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes(B, N), "d2h_bytes_per_step": fe.d2h_bytes(B, N),
                     "ms_per_step": ems / K},
-            "roofline": roof, "kernel_shares": {k: round(v["share"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+            "roofline": roof, "point_ops": point_ops, "kernel_shares": {k: round(v["share"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
 
     if not args.no_cpu_baseline and world == 1:
         import torch as _t

@@ -515,6 +515,77 @@ group_scalar_kernel(const float* __restrict__ feat, const int* __restrict__ idx,
         if (c0 + c < C) o[(size_t)c * MS] = __ldg(f + (size_t)c * N + id);
 }
 
+// Shared-memory staged variants: the GC source rows feat[b, c0 .. c0+GC, :] (N floats each) are brought in once per
+// CTA by the TMA engine (cp.async.bulk), the random 4-byte gathers then hit shared memory instead of L1/L2, and the
+// output leaves as coalesced streaming float4 stores -- the kernel runs at the speed of its (compulsory) write stream.
+constexpr int STAGE_GC = 2;
+constexpr int STAGE_T = 512;
+
+__global__ void __launch_bounds__(STAGE_T)
+group_staged_kernel(const float* __restrict__ feat, const int* __restrict__ idx, int C, int N, int MS4, int chunk4,
+                    float* __restrict__ out) {
+    extern __shared__ __align__(128) float srow[];   // [STAGE_GC][N]
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.z, c0 = blockIdx.y * STAGE_GC;
+    const int nc = min(STAGE_GC, C - c0);
+    if (threadIdx.x == 0) {
+        ssf_mbar_init(&bar, 1);
+        ssf_mbar_fence_init();
+        ssf_mbar_expect_tx(&bar, (uint32_t)nc * (uint32_t)N * 4u);
+        for (int c = 0; c < nc; ++c) ssf_bulk_g2s(srow + (size_t)c * N, feat + ((size_t)b * C + c0 + c) * N, (uint32_t)N * 4u, &bar);
+    }
+    __syncthreads();
+    ssf_mbar_wait(&bar, 0);
+    const int j_end = min(MS4, (int)(blockIdx.x + 1) * chunk4);
+    const int4* ip = reinterpret_cast<const int4*>(idx) + (size_t)b * MS4;
+    float4* o = reinterpret_cast<float4*>(out) + ((size_t)b * C + c0) * MS4;
+    for (int j4 = blockIdx.x * chunk4 + threadIdx.x; j4 < j_end; j4 += STAGE_T) {
+        const int4 id = __ldg(ip + j4);
+#pragma unroll
+        for (int c = 0; c < STAGE_GC; ++c)
+            if (c < nc) {
+                const float* r = srow + (size_t)c * N;
+                __stcs(o + (size_t)c * MS4 + j4, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+            }
+    }
+}
+
+__global__ void __launch_bounds__(STAGE_T)
+three_interpolate_staged_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const float* __restrict__ w, int C,
+                                int M, int N, int chunk, float* __restrict__ out) {
+    extern __shared__ __align__(128) float srow[];   // [STAGE_GC][M]
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.z, c0 = blockIdx.y * STAGE_GC;
+    const int nc = min(STAGE_GC, C - c0);
+    if (threadIdx.x == 0) {
+        ssf_mbar_init(&bar, 1);
+        ssf_mbar_fence_init();
+        ssf_mbar_expect_tx(&bar, (uint32_t)nc * (uint32_t)M * 4u);
+        for (int c = 0; c < nc; ++c) ssf_bulk_g2s(srow + (size_t)c * M, feat + ((size_t)b * C + c0 + c) * M, (uint32_t)M * 4u, &bar);
+    }
+    __syncthreads();
+    ssf_mbar_wait(&bar, 0);
+    const int n_end = min(N, (int)(blockIdx.x + 1) * chunk);
+    for (int n = blockIdx.x * chunk + threadIdx.x; n < n_end; n += STAGE_T) {
+        const int* ip = idx + ((size_t)b * N + n) * 3;
+        const float* wp = w + ((size_t)b * N + n) * 3;
+        const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+        const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+#pragma unroll
+        for (int c = 0; c < STAGE_GC; ++c)
+            if (c < nc) {
+                const float* r = srow + (size_t)c * M;
+                __stcs(out + ((size_t)b * C + c0 + c) * N + n,
+                       __fadd_rn(__fadd_rn(__fmul_rn(r[i0], w0), __fmul_rn(r[i1], w1)), __fmul_rn(r[i2], w2)));
+            }
+    }
+}
+
+// rows of `len` floats can be staged when they are 16-byte granular / aligned and STAGE_GC of them fit in shared memory
+static bool can_stage(const float* feat, int len) {
+    return (len % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) && ((size_t)len * 4 * STAGE_GC <= 200 * 1024);
+}
+
 extern "C" int ssf_grouping_operation(const float* feat, const int* idx, int B, int C, int N, int M, int S, float* out,
                                       void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -522,7 +593,21 @@ extern "C" int ssf_grouping_operation(const float* feat, const int* idx, int B, 
     if (B <= 0 || C <= 0 || MS <= 0) return ssf_arg_error("grouping_operation: empty input");
     const bool vec = (MS % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    if (vec) {
+    if (vec && can_stage(feat, N) && MS >= 4 * N) {
+        // enough outputs per staged row to amortise the staging (each CTA produces >= 4 outputs per staged element)
+        const int MS4 = (int)(MS / 4);
+        const size_t smem = (size_t)N * 4 * STAGE_GC;
+        int chunk4 = MS4;                                  // float4 outputs per CTA: at least N (4N outputs per channel)
+        while (chunk4 / 2 >= N && chunk4 % 2 == 0) chunk4 /= 2;
+        static size_t attr = 0;
+        if (smem > attr) {
+            cudaError_t e = cudaFuncSetAttribute(group_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return ssf_set_error(e);
+            attr = 200 * 1024;
+        }
+        dim3 grid((MS4 + chunk4 - 1) / chunk4, (C + STAGE_GC - 1) / STAGE_GC, B);
+        group_staged_kernel<<<grid, STAGE_T, smem, st>>>(feat, idx, C, N, MS4, chunk4, out);
+    } else if (vec) {
         const int MS4 = (int)(MS / 4);
         dim3 grid((MS4 + 255) / 256, (C + GROUP_CH - 1) / GROUP_CH, B);
         group_vec4_kernel<<<grid, 256, 0, st>>>(feat, idx, C, N, MS4, out);
@@ -566,6 +651,22 @@ extern "C" int ssf_three_interpolate(const float* feat, const int* idx, const fl
                                      float* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || C <= 0 || N <= 0) return ssf_arg_error("three_interpolate: empty input");
+    if (can_stage(feat, M) && N >= M) {
+        const size_t smem = (size_t)M * 4 * STAGE_GC;
+        int chunk = N;
+        while (chunk / 2 >= M && chunk % 2 == 0) chunk /= 2;
+        static size_t attr = 0;
+        if (smem > attr) {
+            cudaError_t e = cudaFuncSetAttribute(three_interpolate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return ssf_set_error(e);
+            attr = 200 * 1024;
+        }
+        dim3 grid((N + chunk - 1) / chunk, (C + STAGE_GC - 1) / STAGE_GC, B);
+        three_interpolate_staged_kernel<<<grid, STAGE_T, smem, st>>>(feat, idx, weight, C, M, N, chunk, out);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
     dim3 grid((N + 255) / 256, (C + GROUP_CH - 1) / GROUP_CH, B);
     three_interpolate_kernel<<<grid, 256, 0, st>>>(feat, idx, weight, C, M, N, out);
     ssf_count_launch();

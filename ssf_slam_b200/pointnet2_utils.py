@@ -61,8 +61,16 @@ def knn(k, unknown, known, offset=None):
     dist = torch.empty(B, Nq, k, dtype=torch.float32, device=unknown.device)
     idx = torch.empty(B, Nq, k, dtype=torch.int32, device=unknown.device)
     off = None if offset is None else _f32(offset)
-    nat.check(nat.lib().ssf_knn_offset(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(known), B, Nq, Nr, nat.ptr(dist),
-                                       nat.ptr(idx), nat.stream()))
+    L = nat.lib()
+    if 512 <= Nr <= 16384:
+        # Morton-block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster
+        ws = torch.empty(int(L.ssf_knn_blocks_workspace_floats(B, Nr)), dtype=torch.float32, device=unknown.device)
+        nat.check(L.ssf_knn_blocks_build(nat.ptr(known), B, Nr, nat.ptr(ws), nat.stream()))
+        nat.check(L.ssf_knn_blocks_search(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(ws), B, Nq, Nr, nat.ptr(dist),
+                                          nat.ptr(idx), nat.stream()))
+        return dist, idx
+    nat.check(L.ssf_knn_offset(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(known), B, Nq, Nr, nat.ptr(dist),
+                                nat.ptr(idx), nat.stream()))
     return dist, idx
 
 

@@ -172,3 +172,24 @@ def test_frontend_pipeline_host_buffers(setup, golden_dir):
     want = ofe.masker_spec(g["pos1"], flow, 0.10)  # mask/pose spec on the very flow the GPU produced
     assert np.array_equal(out["mask"][0].numpy(), want["mask"])
     assert np.array_equal(out["odom"][0].numpy(), want["odom"])
+
+
+def test_tflow_n16384_tensor_core_vs_simt_path(setup):
+    """BASELINE config 3 size (N = 16384, no oracle golden at this size): the tensor-core realisation and the SIMT fp32
+    realisation of the dense layers must give the same FPS indices and flows within the north-star tolerance."""
+    from ssf_slam_b200 import functional as F_, synth
+    it = synth.make_sequence(2000, 1, 16384)[0]
+    pc1 = torch.from_numpy(it["pos1"].T.copy()).unsqueeze(0).cuda()
+    pc2 = torch.from_numpy(it["pos2"].T.copy()).unsqueeze(0).cuda()
+    net = setup["net"]
+    flows_tc, fps_tc = net(pc1, pc2)
+    F_.USE_TC = False
+    try:
+        flows_ref, fps_ref = net(pc1, pc2)
+    finally:
+        F_.USE_TC = True
+    for a, b in zip(fps_tc, fps_ref):
+        assert torch.equal(a, b)
+    errs = [float((a - b).abs().max()) for a, b in zip(flows_tc, flows_ref)]
+    print("N=16384 tensor-core vs SIMT flow max-abs diff per level:", errs)
+    assert flows_tc[0].shape == (1, 3, 16384) and max(errs) <= FLOW_TOL

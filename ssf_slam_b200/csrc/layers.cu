@@ -736,12 +736,16 @@ extern "C" int ssf_cost_volume(const float* Gab, const float* Hab, const float* 
 // ------------------------------------------------- backward cost: segmented softmax-weighted sum
 
 // cost_bwd[j, :] = sum_{l in seg(j)} softmax_seg(logit)[l] * val[l, :]     (soflow.py:471-481, one fused pass)
-// One warp per target point j; rows of a segment are visited in ascending l (deterministic).
-__global__ void __launch_bounds__(128)
+// One warp per target point j.  The softmax weights of up to 32 rows are computed lane-parallel (one expf and one
+// division per row), then broadcast row by row while every lane accumulates its channels with coalesced vector loads.
+// Rows are visited in ascending l and every reduction has a fixed shape, so the result is deterministic.
+template <int VEC>
+__global__ void __launch_bounds__(256)
 seg_softmax_sum_kernel(const float* __restrict__ logit, const float* __restrict__ val, const int* __restrict__ ws, int B,
                        int L, int C, int n_seg, float* __restrict__ out) {
+    constexpr int MAXV = 8;   // channels per lane: C <= 256
     const int b = blockIdx.y;
-    const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= n_seg) return;
     const int* off = ws + (size_t)b * (n_seg + 1);
@@ -753,23 +757,61 @@ seg_softmax_sum_kernel(const float* __restrict__ logit, const float* __restrict_
     for (int a = lo + lane; a < hi; a += 32) mx = fmaxf(mx, lg[rows[a]]);
     mx = ssf_warp_max(mx);
     float den = 0.f;
-    for (int a = lo; a < hi; ++a) den += expf(lg[rows[a]] - mx);  // ascending order on every lane
-    for (int c = lane; c < C; c += 32) {
-        float acc = 0.f;
-        for (int a = lo; a < hi; ++a) {
-            const int r = rows[a];
-            const float w = expf(lg[r] - mx) / den;
-            acc += v[(size_t)r * C + c] * w;
+    for (int base = lo; base < hi; base += 32) {   // batches in ascending order, fixed-shape tree inside a batch
+        const int a = base + lane;
+        den += ssf_warp_sum(a < hi ? expf(lg[rows[a]] - mx) : 0.f);
+    }
+    float acc[MAXV];
+#pragma unroll
+    for (int q = 0; q < MAXV; ++q) acc[q] = 0.f;
+    for (int base = lo; base < hi; base += 32) {
+        const int a = base + lane;
+        int r_l = 0;
+        float w_l = 0.f;
+        if (a < hi) {
+            r_l = rows[a];
+            w_l = expf(lg[r_l] - mx) / den;
         }
-        out[((size_t)b * n_seg + j) * C + c] = acc;
+        const int nb = min(32, hi - base);
+        for (int t = 0; t < nb; ++t) {
+            const int r = __shfl_sync(0xffffffffu, r_l, t);
+            const float w = __shfl_sync(0xffffffffu, w_l, t);
+            const float* vr = v + (size_t)r * C;
+#pragma unroll
+            for (int q = 0; q < MAXV / VEC; ++q) {
+                const int c = (q * 32 + lane) * VEC;
+                if (c < C) {
+                    if (VEC == 2) {
+                        const float2 x = __ldg(reinterpret_cast<const float2*>(vr + c));
+                        acc[q * 2] += x.x * w;
+                        acc[q * 2 + 1] += x.y * w;
+                    } else {
+                        acc[q] += __ldg(vr + c) * w;
+                    }
+                }
+            }
+        }
+    }
+    float* o = out + ((size_t)b * n_seg + j) * C;
+#pragma unroll
+    for (int q = 0; q < MAXV / VEC; ++q) {
+        const int c = (q * 32 + lane) * VEC;
+        if (c < C) {
+            if (VEC == 2) *reinterpret_cast<float2*>(o + c) = make_float2(acc[q * 2], acc[q * 2 + 1]);
+            else o[c] = acc[q];
+        }
     }
 }
 
 extern "C" int ssf_segment_softmax_sum(const float* logit, const float* val, const int* csr_ws, int B, int L, int C,
                                        int n_seg, float* out, void* stream) {
     if (B <= 0 || L <= 0 || C <= 0 || n_seg <= 0) return ssf_arg_error("segment_softmax_sum: empty input");
-    dim3 grid((n_seg + 3) / 4, B);
-    seg_softmax_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(logit, val, csr_ws, B, L, C, n_seg, out);
+    if (C > 256) return ssf_arg_error("segment_softmax_sum: at most 256 channels");
+    dim3 grid((n_seg + 7) / 8, B);
+    if (C % 2 == 0 && (reinterpret_cast<uintptr_t>(val) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
+        seg_softmax_sum_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(logit, val, csr_ws, B, L, C, n_seg, out);
+    else
+        seg_softmax_sum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(logit, val, csr_ws, B, L, C, n_seg, out);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

@@ -737,21 +737,40 @@ __global__ void csr_fill_kernel(const IdxT* __restrict__ key, int L, int n_seg, 
     rows[(size_t)b * L + offset[(size_t)b * (n_seg + 1) + k] + pos] = l;
 }
 
-__global__ void csr_sort_kernel(const int* __restrict__ offset, int n_seg, int L, int* __restrict__ rows) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// rows of every segment into ascending order (the fill above lands them in atomic order).  One warp per segment:
+// segments of <= 32 rows (the common case: 16 on average) are sorted across the lanes by a bitonic network, longer ones
+// by an insertion sort on lane 0.
+__global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ offset, int n_seg, int L, int* __restrict__ rows) {
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     if (j >= n_seg) return;
     const int* off = offset + (size_t)b * (n_seg + 1);
     int* r = rows + (size_t)b * L;
-    const int lo = off[j], hi = off[j + 1];
-    for (int a = lo + 1; a < hi; ++a) {
-        const int v = r[a];
-        int p = a - 1;
-        while (p >= lo && r[p] > v) {
-            r[p + 1] = r[p];
-            --p;
+    const int lo = off[j], hi = off[j + 1], cnt = hi - lo;
+    if (cnt <= 1) return;
+    if (cnt <= 32) {
+        int v = lane < cnt ? r[lo + lane] : 0x7fffffff;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                const int o = __shfl_xor_sync(0xffffffffu, v, jj);
+                const bool take_min = ((lane & jj) == 0) == ((lane & kk) == 0);
+                v = take_min ? min(v, o) : max(v, o);
+            }
         }
-        r[p + 1] = v;
+        if (lane < cnt) r[lo + lane] = v;
+    } else if (lane == 0) {
+        for (int a = lo + 1; a < hi; ++a) {
+            const int v = r[a];
+            int p = a - 1;
+            while (p >= lo && r[p] > v) {
+                r[p + 1] = r[p];
+                --p;
+            }
+            r[p + 1] = v;
+        }
     }
 }
 
@@ -771,8 +790,8 @@ static int build_csr(const IdxT* key, int B, int L, int n_seg, int* ws, cudaStre
     csr_count_kernel<IdxT><<<gl, 256, 0, st>>>(key, L, n_seg, offset);
     csr_scan_kernel<<<B, 1024, 0, st>>>(offset, n_seg);
     csr_fill_kernel<IdxT><<<gl, 256, 0, st>>>(key, L, n_seg, offset, cursor, rows);
-    dim3 gs((n_seg + 127) / 128, B);
-    csr_sort_kernel<<<gs, 128, 0, st>>>(offset, n_seg, L, rows);
+    dim3 gs((n_seg + 7) / 8, B);
+    csr_sort_kernel<<<gs, 256, 0, st>>>(offset, n_seg, L, rows);
     for (int i = 0; i < 4; ++i) ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

@@ -166,3 +166,26 @@ def test_knn_blocks_equals_brute_force(B, Nq, Nr, k, dup, off):
     torch.cuda.synchronize()
     assert torch.equal(i0, i1)
     assert torch.equal(d0, d1)
+
+
+@pytest.mark.parametrize("B,L,C,n_seg,hot", [(2, 4096, 64, 300, False), (1, 3000, 128, 50, True), (2, 1000, 5, 400, False), (1, 64, 256, 7, True)])
+def test_segment_softmax_sum_fused(B, L, C, n_seg, hot):
+    """Backward-cost kernel (softmax over each segment's logits, weighted sum of its rows) vs the dense definition;
+    `hot` concentrates rows on a few keys so that segments exceed one warp batch (32 rows)."""
+    import torch
+    from ssf_slam_b200 import functional as F_
+    g = torch.Generator().manual_seed(L + C)
+    key = torch.randint(0, 3 if hot else n_seg, (B, L), generator=g, dtype=torch.int32)
+    logit = torch.randn(B, L, generator=g) * 3
+    val = torch.randn(B, L, C, generator=g)
+    csr = F_.build_csr(key.cuda(), n_seg)
+    got = F_.segment_softmax_sum(logit.cuda(), val.cuda().contiguous(), csr, n_seg).cpu().double()
+    want = torch.zeros(B, n_seg, C, dtype=torch.float64)
+    for b in range(B):
+        for j in key[b].unique().tolist():
+            m = key[b] == j
+            w = torch.softmax(logit[b][m].double(), dim=0)
+            want[b, j] = (w[:, None] * val[b][m].double()).sum(0)
+    assert float((got - want).abs().max()) < 1e-5
+    again = F_.segment_softmax_sum(logit.cuda(), val.cuda().contiguous(), F_.build_csr(key.cuda(), n_seg), n_seg).cpu().double()
+    assert torch.equal(got, again)   # deterministic

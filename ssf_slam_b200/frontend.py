@@ -66,13 +66,34 @@ def background_index(points, flow, sem=None, inst=None, movable=(), tau=0.10, de
     return odometry(points, flow, sem=sem, inst=inst, movable=movable, tau=tau, device=device)["bg_index"]
 
 
-class SceneFlowFrontEnd:
-    """Scene flow + dynamic mask + ego-motion for batches of frame pairs in host memory."""
+class _Pending:
+    """Result of ``SceneFlowFrontEnd.submit``: pinned host buffers that are valid once the recorded event has completed."""
 
-    def __init__(self, net, device="cuda:0", tau=0.10, movable=()):
+    def __init__(self, event, out):
+        self._event, self._out = event, out
+
+    def result(self):
+        self._event.synchronize()
+        return self._out
+
+
+class SceneFlowFrontEnd:
+    """Scene flow + dynamic mask + ego-motion for batches of frame pairs in host memory.
+
+    ``process`` is the synchronous call.  ``submit(..., slot=i)`` runs the same work on the i-th of ``n_slots`` private CUDA
+    streams with private pinned staging buffers and returns immediately; independent batches submitted to different slots
+    overlap on the GPU (one batch's H2D / D2H copies and its latency-bound kernels such as FPS run under the other's dense
+    kernels).  Frame pairs are independent (ASF/main_sju_occ_ros.py:168-284), so this is plain pipelining."""
+
+    def __init__(self, net, device="cuda:0", tau=0.10, movable=(), n_slots=2):
         nat.require_device()
         self.net, self.device, self.tau, self.movable = net, torch.device(device), tau, tuple(movable)
         self._pin = {}
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n_slots)]
+        self._pending = [None] * n_slots
+        if hasattr(net, "weights"):   # prepare the kernel-side weight images once, before any slot stream can race on them
+            net.weights(self.device)
+            torch.cuda.synchronize(self.device)
 
     def _staged(self, name, arr, dtype):
         """host array -> pinned staging buffer -> device (async on the current stream)."""
@@ -83,19 +104,41 @@ class SceneFlowFrontEnd:
         self._pin[key].copy_(t)
         return self._pin[key].to(self.device, non_blocking=True)
 
+    def _host_out(self, name, t):
+        key = (name, tuple(t.shape), t.dtype)
+        if key not in self._pin:
+            self._pin[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        self._pin[key].copy_(t, non_blocking=True)
+        return self._pin[key]
+
     @torch.no_grad()
+    def submit(self, pos1, pos2, sem=None, inst=None, n_inst=0, return_flow=False, slot=0):
+        """Asynchronous ``process`` on slot ``slot``; returns a handle whose ``.result()`` yields the same dict.  The
+        buffers of a slot are reused by its next submit, which first waits for the previous one."""
+        if self._pending[slot] is not None:
+            self._pending[slot].result()   # staging buffers of this slot are free again
+        st = self._streams[slot]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            tag = "s%d." % slot
+            x1 = self._staged(tag + "p1", pos1, torch.float32)
+            x2 = self._staged(tag + "p2", pos2, torch.float32)
+            ts = None if sem is None else self._staged(tag + "sem", sem, torch.int32)
+            ti = None if inst is None else self._staged(tag + "inst", inst, torch.int32)
+            flows, _ = self.net.forward_pm(x1, x2)
+            mask, odom = F_.frontend(x1, flows[0], mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
+            out = dict(mask=self._host_out(tag + "mask", mask), odom=self._host_out(tag + "odom", odom))
+            if return_flow:
+                out["flow"] = self._host_out(tag + "flow", flows[0])
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._pending[slot] = _Pending(ev, out)
+        return self._pending[slot]
+
     def process(self, pos1, pos2, sem=None, inst=None, n_inst=0, return_flow=False):
-        """pos1, pos2: host f32 [B,N,3] -> dict(mask u8 [B,N], odom f64 [B,7] (, flow f32 [B,N,3])) on the host."""
-        x1 = self._staged("p1", pos1, torch.float32)
-        x2 = self._staged("p2", pos2, torch.float32)
-        ts = None if sem is None else self._staged("sem", sem, torch.int32)
-        ti = None if inst is None else self._staged("inst", inst, torch.int32)
-        flows, _ = self.net.forward_pm(x1, x2)
-        mask, odom = F_.frontend(x1, flows[0], mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
-        out = dict(mask=mask.cpu(), odom=odom.cpu())
-        if return_flow:
-            out["flow"] = flows[0].cpu()
-        return out
+        """pos1, pos2: host f32 [B,N,3] -> dict(mask u8 [B,N], odom f64 [B,7] (, flow f32 [B,N,3])) on the host
+        (pinned buffers owned by this object, overwritten by the next call on the same slot)."""
+        return self.submit(pos1, pos2, sem=sem, inst=inst, n_inst=n_inst, return_flow=return_flow, slot=0).result()
 
     def h2d_bytes(self, B, N, seg=False):
         return B * N * 3 * 4 * 2 + (B * N * 4 * 2 if seg else 0)

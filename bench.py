@@ -328,13 +328,15 @@ def main():
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     ems = float(ems.item())
 
-    # ---- per-kernel shares (CUDA events around every launch of ours, same workload, after the timed region)
-    prof.enable()
-    for s in range(min(K, 3)):
-        device_step(Wm + s, keep)
-    torch.cuda.synchronize()
-    shares = prof.summary()
-    prof.disable()
+    # ---- per-kernel shares (CUDA events around every launch of ours, same workload, after the timed region; on one of the
+    # pipeline streams so that the caching allocator's warm pool is used: a cold pool would put cudaMalloc inside the events)
+    with torch.cuda.stream(streams[0]):
+        prof.enable()
+        for s in range(min(K, 3)):
+            device_step(Wm + s, keep)
+        torch.cuda.synchronize()
+        shares = prof.summary()
+        prof.disable()
     keep.clear()
 
     point_ops = point_op_rooflines(B, N, dev) if rank == 0 else None

@@ -158,6 +158,10 @@ int ssf_frontend(const float* points, const float* flow, int B, int N, int mode,
 int ssf_tc_gemm_test(const float* X, const float* Whi_img, const float* Wlo_img, int K, int N, int mode, int passes,
                      float* Y, void* stream);
 
+/* tensor-pipe pacing probe (developer tool): cycles for `reps` back-to-back M128 x N x K8 kind::tf32 MMAs, A operand from
+ * TMEM (mode 0) or shared memory (mode 1), acc_bufs accumulators round-robin; out[0] = total cycles, out[1] = issue cycles */
+int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

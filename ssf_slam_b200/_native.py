@@ -53,6 +53,7 @@ SIGNATURES = {
     "ssf_dense_args_bytes": ("", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
     "ssf_tc_gemm_test": ("pppiiiipp", _I),
+    "ssf_tc_mma_rate": ("iiiipp", _I),
 }
 
 

@@ -82,13 +82,13 @@ __device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
     }
 }
 
-// Measured on B200 (scripts/trace_cv.py): one M128 x N64 x K8 kind::tf32 MMA with the A operand in TMEM retires every
-// ~55 cycles whether or not consecutive MMAs share an accumulator (interleaving the two branches' chains changed
-// nothing), i.e. ~1400 cycles per 24-MMA layer and ~14k cycles of tensor time per tile.
+// Issue pacing measured on B200 (scripts/mma_rate.py): 42 cycles per M128 x N64 x K8 kind::tf32 MMA (A in TMEM) when the
+// issuing warp runs warp-uniformly with one elected lane, ~55 in this kernel when it sat in an `if (lane == 0)` region;
+// sharing or alternating accumulators makes no difference.
 // D[128 x N] = A[128 x 64] . W[N x 64]^T, 3xTF32: Alo.Whi + Ahi.Wlo + Ahi.Whi  (one thread).  The shared-memory descriptors
 // of the 8 K-steps differ only in the start-address field, so they are formed by one 64-bit add on a base descriptor.
 template <int N>
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi_smem) {
+__device__ __forceinline__ void issue_gemm(bool leader, uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi_smem) {
     constexpr uint32_t idesc = tc_idesc_tf32(128, N);
     constexpr uint32_t lbo = (uint32_t)(N / 8) * 128;
     const uint64_t d_hi = tc_smem_desc(w_hi_smem, lbo, 128);
@@ -100,6 +100,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint3
 #pragma unroll
         for (int ks = 0; ks < CM / 8; ++ks) {
             const uint64_t bdesc = w + (uint64_t)((ks * 2 * lbo) >> 4);
+            if (!leader) continue;   // whole warp runs the (uniform) address arithmetic, one elected lane issues
             if (pass == 0 && ks == 0)
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
                              "r"(a + ks * 8), "l"(bdesc), "r"(idesc)
@@ -166,8 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
         }
         __syncwarp();
     } else if (warp == 16) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane issues)
+        {
+            const bool leader = tc_elect_one();
             uint32_t in_phase = 0;
             for (int it = 0; it < n_my; ++it) {
                 for (int step = 0; step < 5; ++step) {
@@ -177,14 +179,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
                         if (step == 0 || br == 0) ssf_mbar_wait(&w_full[st], (uint32_t)((g / NSTAGE) & 1));
                         ssf_mbar_wait(&in_ready[br], in_phase);
                         tc_fence_after();
-                        { const bool trace_me = true; TRACE(2, step * 4 + br * 2); }
+                        { const bool trace_me = lane == 0; TRACE(2, step * 4 + br * 2); }
                         const uint32_t in_hi = tmem + T_IN + br * 128;
                         const uint32_t d = tmem + (step == 2 ? T_C : T_D) + br * 64;
-                        if (step == 4) issue_gemm<32>(d, in_hi, in_hi + 64, ssf_smem_u32(sWst + st * STAGE_BYTES));
-                        else issue_gemm<64>(d, in_hi, in_hi + 64, ssf_smem_u32(sWst + st * STAGE_BYTES));
-                        tc_commit(&d_ready[br]);
-                        if (step == 0 || br == 1) tc_commit(&w_empty[st]);
-                        { const bool trace_me = true; TRACE(2, step * 4 + br * 2 + 1); }
+                        if (step == 4) issue_gemm<32>(leader, d, in_hi, in_hi + 64, ssf_smem_u32(sWst + st * STAGE_BYTES));
+                        else issue_gemm<64>(leader, d, in_hi, in_hi + 64, ssf_smem_u32(sWst + st * STAGE_BYTES));
+                        if (leader) {
+                            tc_commit(&d_ready[br]);
+                            if (step == 0 || br == 1) tc_commit(&w_empty[st]);
+                        }
+                        __syncwarp();
+                        { const bool trace_me = lane == 0; TRACE(2, step * 4 + br * 2 + 1); }
                     }
                     in_phase ^= 1;
                 }

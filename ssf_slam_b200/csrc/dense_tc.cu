@@ -150,9 +150,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
         }
         __syncwarp();
     } else if (warp == 12) {
-        if (lane == 0) {   // ---- MMA issuer
+        {   // ---- MMA issuer: warp-uniform control flow, one elected lane executes the tcgen05 instructions
+            const bool leader = tc_elect_one();
             const uint32_t idesc = tc_idesc_tf32(128, Nt);
             const uint32_t lbo = (uint32_t)(Nt / 8) * 128;
+            const uint64_t lo_off = (uint64_t)(((uint32_t)Nt * KC * 4) >> 4), k_step = (uint64_t)((2 * lbo) >> 4);
             for (int it = 0; it < n_my; ++it) {
                 const int db = it % cfg.nd;
                 if (it >= cfg.nd) {
@@ -171,21 +173,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
                     }
                     ssf_mbar_wait(&a_ready[as], (uint32_t)((j >> 1) & 1));
                     tc_fence_after();
-                    const uint32_t w_hi = ssf_smem_u32(sW + (size_t)ws * wchunk), w_lo = w_hi + (uint32_t)Nt * KC * 4;
-                    const uint32_t a_hi = tmem + a_col0 + as * 64, a_lo = a_hi + 32;
+                    // the descriptors of the 4 K-steps / hi-lo images differ only in the start-address field
+                    const uint64_t w_hi = tc_smem_desc(ssf_smem_u32(sW + (size_t)ws * wchunk), lbo, 128);
+                    const uint32_t a_hi = tmem + a_col0 + as * 64;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t aa = pass == 0 ? a_lo : a_hi;
-                        const uint32_t ww = pass == 1 ? w_lo : w_hi;
+                        const uint32_t aa = a_hi + (pass == 0 ? 32u : 0u);
+                        const uint64_t ww = w_hi + (pass == 1 ? lo_off : 0);
 #pragma unroll
                         for (int ks = 0; ks < KC / 8; ++ks)
-                            tc_mma_ts(d_tmem, aa + ks * 8, tc_smem_desc(ww + ks * 2 * lbo, lbo, 128), idesc,
-                                      (kc > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                            if (leader) tc_mma_ts(d_tmem, aa + ks * 8, ww + ks * k_step, idesc, (kc > 0 || pass > 0 || ks > 0) ? 1u : 0u);
                     }
-                    tc_commit(&a_empty[as]);
-                    if (!cfg.resident) tc_commit(&w_empty[ws]);
+                    if (leader) {
+                        tc_commit(&a_empty[as]);
+                        if (!cfg.resident) tc_commit(&w_empty[ws]);
+                    }
+                    __syncwarp();
                 }
-                tc_commit(&d_full[db]);
+                if (leader) tc_commit(&d_full[db]);
+                __syncwarp();
             }
         }
         __syncwarp();

@@ -64,6 +64,16 @@ __device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a fully converged warp (elect.sync).  MMA-issuing warps run their control flow warp-uniformly and predicate
+// only the tcgen05 instructions on this flag: descriptor arithmetic then stays in uniform registers.  Measured on B200
+// (scripts/mma_rate.py): 42 cycles per M128 x N64 x K8 kind::tf32 MMA this way (N/2 + ~10) against ~200 cycles when the
+// issuing code sits inside a divergent `if (lane == 0)` region.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(is_leader));
+    return is_leader != 0;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");

@@ -102,3 +102,83 @@ extern "C" int ssf_tc_gemm_test(const float* X, const float* Whi_img, const floa
     SSF_LAUNCH_CHECK();
     return SSF_OK;
 }
+
+// ---- tensor-pipe pacing probe: `reps` back-to-back kind::tf32 MMAs (M128 x N x K8) from one thread, operands zero.
+// mode 0: A from TMEM, 1: A from shared memory; acc_bufs accumulators used round-robin.  out[0] = cycles from first issue
+// to completion (commit -> mbarrier), out[1] = cycles spent issuing.
+__global__ void __launch_bounds__(128) tc_mma_rate_kernel(int N, int mode, int reps, int acc_bufs, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (N * 8 + 128 * 8) * 4 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
+    if (warp == 0) tc_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        ssf_mbar_init(&bar, 1);
+        ssf_mbar_fence_init();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (mode < 2) {
+        if (tid == 0) {   // divergent single-thread issue (what `if (lane == 0)` role code compiles to)
+            const uint32_t idesc = tc_idesc_tf32(128, N);
+            const uint32_t lboW = (uint32_t)(N / 8) * 128, lboA = 16 * 128;
+            const uint64_t bdesc = tc_smem_desc(ssf_smem_u32(smem), lboW, 128);
+            const uint64_t adesc = tc_smem_desc(ssf_smem_u32(smem + N * 8 * 4), lboA, 128);
+            const long long t0 = clock64();
+            for (int i = 0; i < reps; ++i) {
+                const uint32_t d = tmem + (uint32_t)((i % acc_bufs) * N);
+                if (mode == 0) tc_mma_ts(d, tmem + 496, bdesc, idesc, 1);
+                else tc_mma_ss(d, adesc, bdesc, idesc, 1);
+            }
+            const long long t1 = clock64();
+            tc_commit(&bar);
+            ssf_mbar_wait(&bar, 0);
+            const long long t2 = clock64();
+            out[0] = t2 - t0;
+            out[1] = t1 - t0;
+        }
+    } else if (warp == 0) {
+        // warp-uniform issue: every lane runs the loop, one elected lane executes the MMA.  Address arithmetic stays in
+        // uniform registers (no per-instruction R2UR), the loop is unrolled by 8 with the K-step baked into the descriptor.
+        uint32_t is_leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(is_leader));
+        const uint32_t idesc = tc_idesc_tf32(128, N);
+        const uint32_t lboW = (uint32_t)(N / 8) * 128, lboA = 16 * 128;
+        const uint64_t bdesc = tc_smem_desc(ssf_smem_u32(smem), lboW, 128);
+        const uint64_t adesc = tc_smem_desc(ssf_smem_u32(smem + N * 8 * 4), lboA, 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t d = tmem + (uint32_t)((u % 2) * (acc_bufs - 1) * N);
+                if (is_leader) {
+                    if (mode == 2) tc_mma_ts(d, tmem + 496, bdesc, idesc, 1);
+                    else tc_mma_ss(d, adesc, bdesc, idesc, 1);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if (is_leader) tc_commit(&bar);
+        ssf_mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (is_leader) {
+            out[0] = t2 - t0;
+            out[1] = t1 - t0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tmem, 512);
+}
+
+extern "C" int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long long* out, void* stream) {
+    if (N % 16 || N < 16 || N > 256 || acc_bufs < 1 || acc_bufs * N > 480) return ssf_arg_error("tc_mma_rate: bad shape");
+    tc_mma_rate_kernel<<<1, 128, (N * 8 + 128 * 8) * 4 + 1024, (cudaStream_t)stream>>>(N, mode, reps, acc_bufs, out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}

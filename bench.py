@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frame pairs in the cpu_baseline sample")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams independent batches are pipelined over")
     ap.add_argument("--shares-out", default=None, help="write the full per-kernel CUDA-event table (JSON) to this path")
     return ap.parse_args()
 
@@ -242,13 +243,14 @@ def main():
     sd = random_init_state_dict(0)
     net = TFlow()
     net.load_state_dict(sd, strict=True)
-    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10)   # also prepares the weight images (synchronised)
+    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=max(1, args.streams))   # also prepares the weight images
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
     dev_batches = [(d1[batch_ids(s)].contiguous(), d2[batch_ids(s)].contiguous()) for s in range(max(1, min(K + Wm, POOL)))]
 
     # Independent batches are pipelined over two CUDA streams (frame pairs carry no cross-batch state): one batch's
     # latency-bound kernels (FPS: 128 CTAs x 1.7 ms) and persistent-kernel tails run under the other batch's dense kernels.
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    NS = max(1, args.streams)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
 
     def device_step(s, keep, stream=None):
         x1, x2 = dev_batches[s % len(dev_batches)]
@@ -269,7 +271,7 @@ def main():
     # ---- device-resident throughput
     keep = []
     for s in range(Wm):
-        device_step(s, keep, streams[s % 2])
+        device_step(s, keep, streams[s % NS])
     sync_all()
     keep.clear()
     clocks = ClockSampler(local)
@@ -282,7 +284,7 @@ def main():
     for st in streams:
         st.wait_event(ev0)
     for s in range(K):
-        device_step(Wm + s, keep, streams[s % 2])
+        device_step(Wm + s, keep, streams[s % NS])
     for st in streams:
         main.wait_stream(st)
     if world > 1:  # final gather of poses and masks (the only communication of the job)
@@ -301,8 +303,8 @@ def main():
     host_batches = [(torch.from_numpy(p1[batch_ids(s)]), torch.from_numpy(p2[batch_ids(s)]))
                     for s in range(max(1, min(K + Wm, POOL)))]
     for s in range(Wm):
-        fe.submit(*host_batches[s % len(host_batches)], slot=s % 2)
-    for slot in range(2):
+        fe.submit(*host_batches[s % len(host_batches)], slot=s % NS)
+    for slot in range(NS):
         if fe._pending[slot] is not None:
             fe._pending[slot].result()
     sync_all()
@@ -310,9 +312,9 @@ def main():
     e0.record(main)
     for st in fe._streams:
         st.wait_event(e0)
-    pend = [None, None]
+    pend = [None] * NS
     for s in range(K):
-        slot = s % 2
+        slot = s % NS
         if pend[slot] is not None:
             out = pend[slot].result()
         pend[slot] = fe.submit(*host_batches[(Wm + s) % len(host_batches)], slot=slot)
@@ -383,7 +385,7 @@ def main():
                                    "noSeg_ActiveSceneFlow pipeline (flow + dynamic mask + ego-motion)" % N,
                        "pairs_per_step_per_gpu": B, "distinct_pairs": POOL, "sharding": "sequence id %% world (config 4), no "
                        "collective on the hot path; one final all_gather of poses+masks",
-                       "pipelining": "independent batches alternate over 2 CUDA streams (double-buffered staging in the e2e leg)",
+                       "pipelining": "independent batches alternate over %d CUDA streams (per-stream pinned staging in the e2e leg)" % NS,
                        "l2": "per-step working set (~%.1f GB of intermediates) exceeds the 126 MB L2" % (B * 0.12)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes(B, N), "d2h_bytes_per_step": fe.d2h_bytes(B, N),

@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frame pairs in the cpu_baseline sample")
+    ap.add_argument("--graph", action="store_true", help="e2e / latency legs: CUDA-graph replay of the step instead of eager "
+                    "launches (measured equal on B200: the step is bound by kernel time, not by launch cost)")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams independent batches are pipelined over")
     ap.add_argument("--shares-out", default=None, help="write the full per-kernel CUDA-event table (JSON) to this path")
     return ap.parse_args()
@@ -243,7 +245,7 @@ def main():
     sd = random_init_state_dict(0)
     net = TFlow()
     net.load_state_dict(sd, strict=True)
-    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=max(1, args.streams))   # also prepares the weight images
+    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=max(1, args.streams), use_graph=args.graph)   # also prepares the weight images
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
     dev_batches = [(d1[batch_ids(s)].contiguous(), d2[batch_ids(s)].contiguous()) for s in range(max(1, min(K + Wm, POOL)))]
 
@@ -330,6 +332,18 @@ def main():
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     ems = float(ems.item())
 
+    # ---- single-pair latency (the reference's operating point: one frame pair per 100 ms tick), host buffers in and out,
+    fe1 = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=1, use_graph=args.graph)
+    one = (torch.from_numpy(p1[:1]), torch.from_numpy(p2[:1]))
+    for _ in range(5):
+        fe1.process(*one)
+    torch.cuda.synchronize()
+    t_lat = time.perf_counter()
+    for _ in range(20):
+        fe1.process(*one)
+    latency_ms = (time.perf_counter() - t_lat) / 20 * 1e3
+    del fe1
+
     # ---- per-kernel shares (CUDA events around every launch of ours, same workload, after the timed region; on one of the
     # pipeline streams so that the caching allocator's warm pool is used: a cold pool would put cudaMalloc inside the events)
     with torch.cuda.stream(streams[0]):
@@ -390,6 +404,8 @@ def main():
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes(B, N), "d2h_bytes_per_step": fe.d2h_bytes(B, N),
                     "ms_per_step": ems / K},
+            "latency": {"pairs": 1, "ms_per_pair": latency_ms, "note": "SceneFlowFrontEnd.process on one host-resident frame pair "
+                        "(H2D + %s + D2H), mean of 20" % ("CUDA-graph replay" if args.graph else "eager launches")},
             "roofline": roof, "point_ops": point_ops, "kernel_shares": {k: round(v["share"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
 
     if not args.no_cpu_baseline and world == 1:

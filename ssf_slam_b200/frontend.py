@@ -85,23 +85,28 @@ class SceneFlowFrontEnd:
     overlap on the GPU (one batch's H2D / D2H copies and its latency-bound kernels such as FPS run under the other's dense
     kernels).  Frame pairs are independent (ASF/main_sju_occ_ros.py:168-284), so this is plain pipelining."""
 
-    def __init__(self, net, device="cuda:0", tau=0.10, movable=(), n_slots=2):
+    def __init__(self, net, device="cuda:0", tau=0.10, movable=(), n_slots=2, use_graph=False):
         nat.require_device()
         self.net, self.device, self.tau, self.movable = net, torch.device(device), tau, tuple(movable)
         self._pin = {}
         self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n_slots)]
         self._pending = [None] * n_slots
+        self.use_graph = use_graph
+        self._graphs = {}   # (slot, B, N, seg, return_flow) -> (graph, static inputs, static outputs)
         if hasattr(net, "weights"):   # prepare the kernel-side weight images once, before any slot stream can race on them
             net.weights(self.device)
             torch.cuda.synchronize(self.device)
 
-    def _staged(self, name, arr, dtype):
-        """host array -> pinned staging buffer -> device (async on the current stream)."""
+    def _staged(self, name, arr, dtype, out=None):
+        """host array -> pinned staging buffer -> device (async on the current stream; into `out` when given)."""
         t = torch.as_tensor(arr)
         key = (name, tuple(t.shape), dtype)
         if key not in self._pin:
             self._pin[key] = torch.empty(t.shape, dtype=dtype, pin_memory=True)
         self._pin[key].copy_(t)
+        if out is not None:
+            out.copy_(self._pin[key], non_blocking=True)
+            return out
         return self._pin[key].to(self.device, non_blocking=True)
 
     def _host_out(self, name, t):
@@ -110,6 +115,35 @@ class SceneFlowFrontEnd:
             self._pin[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         self._pin[key].copy_(t, non_blocking=True)
         return self._pin[key]
+
+    def _run(self, x1, x2, ts, ti, n_inst):
+        flows, _ = self.net.forward_pm(x1, x2)
+        mask, odom = F_.frontend(x1, flows[0], mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
+        return flows[0], mask, odom
+
+    def _graph_for(self, slot, B, N, seg, n_inst):
+        """CUDA graph of the whole step (172 kernel launches at N = 8192) for one slot and input shape: static device
+        inputs / outputs, captured after two eager warm-up runs on the slot's stream.  Replaying it removes the per-launch
+        host cost, which dominates single-pair latency (the reference's operating point: one pair per 100 ms)."""
+        key = (slot, B, N, seg, n_inst)
+        if key not in self._graphs:
+            dev = self.device
+            x1 = torch.zeros(B, N, 3, dtype=torch.float32, device=dev)
+            x2 = torch.zeros(B, N, 3, dtype=torch.float32, device=dev)
+            ts = torch.zeros(B, N, dtype=torch.int32, device=dev) if seg else None
+            ti = torch.zeros(B, N, dtype=torch.int32, device=dev) if seg else None
+            # warm-up on well-formed clouds (distinct points) so every lazily initialised path has run before capture
+            g = torch.Generator(device=dev).manual_seed(0)
+            x1.copy_(torch.randn(B, N, 3, device=dev, generator=g) * 20)
+            x2.copy_(x1 + 0.1)
+            for _ in range(2):
+                self._run(x1, x2, ts, ti, n_inst)
+            torch.cuda.current_stream(dev).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=torch.cuda.current_stream(dev)):
+                flow, mask, odom = self._run(x1, x2, ts, ti, n_inst)
+            self._graphs[key] = (graph, (x1, x2, ts, ti), (flow, mask, odom))
+        return self._graphs[key]
 
     @torch.no_grad()
     def submit(self, pos1, pos2, sem=None, inst=None, n_inst=0, return_flow=False, slot=0):
@@ -121,15 +155,24 @@ class SceneFlowFrontEnd:
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st):
             tag = "s%d." % slot
-            x1 = self._staged(tag + "p1", pos1, torch.float32)
-            x2 = self._staged(tag + "p2", pos2, torch.float32)
-            ts = None if sem is None else self._staged(tag + "sem", sem, torch.int32)
-            ti = None if inst is None else self._staged(tag + "inst", inst, torch.int32)
-            flows, _ = self.net.forward_pm(x1, x2)
-            mask, odom = F_.frontend(x1, flows[0], mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
+            if self.use_graph:
+                B, N = int(np.shape(pos1)[0]), int(np.shape(pos1)[1])
+                graph, (g1, g2, gs, gi), (flow, mask, odom) = self._graph_for(slot, B, N, sem is not None, int(n_inst))
+                self._staged(tag + "p1", pos1, torch.float32, out=g1)
+                self._staged(tag + "p2", pos2, torch.float32, out=g2)
+                if sem is not None:
+                    self._staged(tag + "sem", sem, torch.int32, out=gs)
+                    self._staged(tag + "inst", inst, torch.int32, out=gi)
+                graph.replay()
+            else:
+                x1 = self._staged(tag + "p1", pos1, torch.float32)
+                x2 = self._staged(tag + "p2", pos2, torch.float32)
+                ts = None if sem is None else self._staged(tag + "sem", sem, torch.int32)
+                ti = None if inst is None else self._staged(tag + "inst", inst, torch.int32)
+                flow, mask, odom = self._run(x1, x2, ts, ti, n_inst)
             out = dict(mask=self._host_out(tag + "mask", mask), odom=self._host_out(tag + "odom", odom))
             if return_flow:
-                out["flow"] = self._host_out(tag + "flow", flows[0])
+                out["flow"] = self._host_out(tag + "flow", flow)
             ev = torch.cuda.Event()
             ev.record(st)
         self._pending[slot] = _Pending(ev, out)

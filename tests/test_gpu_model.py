@@ -193,3 +193,17 @@ def test_tflow_n16384_tensor_core_vs_simt_path(setup):
     errs = [float((a - b).abs().max()) for a, b in zip(flows_tc, flows_ref)]
     print("N=16384 tensor-core vs SIMT flow max-abs diff per level:", errs)
     assert flows_tc[0].shape == (1, 3, 16384) and max(errs) <= FLOW_TOL
+
+
+def test_frontend_cuda_graph_replay_equals_eager(setup, golden_dir):
+    """The captured CUDA graph of the whole step gives the same masks / poses / flows as the eager launches, for
+    several different inputs replayed through the same graph."""
+    from ssf_slam_b200 import synth
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    eager = SceneFlowFrontEnd(setup["net"], tau=0.10)
+    graph = SceneFlowFrontEnd(setup["net"], tau=0.10, use_graph=True)
+    for seed in (11, 12, 13):
+        it = synth.make_pair(seed, 2048)
+        a = {k: v.clone() for k, v in eager.process(it["pos1"][None], it["pos2"][None], return_flow=True).items()}
+        b = graph.process(it["pos1"][None], it["pos2"][None], return_flow=True)
+        assert torch.equal(a["mask"], b["mask"]) and torch.equal(a["odom"], b["odom"]) and torch.equal(a["flow"], b["flow"])

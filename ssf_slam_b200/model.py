@@ -29,6 +29,28 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = F_.ACT_NONE, F_.ACT_RELU, F_.ACT_LEAKY
 # --------------------------------------------------------------------------- parameter holders
 # (names mirror the reference module tree so that state_dict keys are identical)
 
+class _OwnWeights:
+    """Layer objects used on their own (the B-layer boundary: reference TFlow code constructing our classes) prepare
+    the kernel operands from their own parameters, once per device / load_state_dict."""
+    _kind = None
+
+    def _own(self, device):
+        cache = getattr(self, "_own_cache", None)
+        if cache is None or cache[0] != device:
+            cache = (device, prepare_block(self._kind, self.state_dict(), device))
+            object.__setattr__(self, "_own_cache", cache)
+        return cache[1]
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        object.__setattr__(self, "_own_cache", None)
+        return super()._load_from_state_dict(*args, **kwargs)
+
+
+def _pm(x):
+    """reference layout [B,C,N] -> point-major [B,N,C] (contiguous fp32)"""
+    return F_.transpose(x.contiguous().float())
+
+
 class _LeakyConv1d(nn.Module):
     """`Conv1d` blocks: `.composed_module.0` is the conv (ASF/TFlowV3_Occlussion.py:22-38 no bias;
     ASF/utils/soflow.py:1260-1276 with bias)."""
@@ -38,8 +60,9 @@ class _LeakyConv1d(nn.Module):
         self.composed_module = nn.Sequential(nn.Conv1d(cin, cout, 1, bias=bias), nn.Identity(), nn.Identity())
 
 
-class PointNetSetAbstraction(nn.Module):
-    """Parameters of ASF/utils/utils.py:185-201 (radius / group_all are accepted and ignored, as there)."""
+class PointNetSetAbstraction(_OwnWeights, nn.Module):
+    """ASF/utils/utils.py:185-248 (radius / group_all are accepted and ignored, as there: the layer groups by kNN)."""
+    _kind = "sa"
 
     def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all=False):
         super().__init__()
@@ -51,10 +74,22 @@ class PointNetSetAbstraction(nn.Module):
             self.mlp_convs.append(nn.Conv2d(last, c, 1, bias=False))
             self.mlp_bns.append(nn.BatchNorm2d(c))
             last = c
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, xyz, points):
+        """xyz [B,3,N], points [B,D,N] -> (new_xyz [B,3,S], new_points [B,mlp[-1],S], fps_idx i32 [B,S])
+        (ASF/utils/utils.py:208-248; eval mode)."""
+        nat.require_device()
+        F_.knn_cache_clear()
+        nx, nf, fi = set_abstraction_pm(self._own(xyz.device), self.npoint, self.nsample, _pm(xyz), _pm(points))
+        F_.knn_cache_clear()
+        return F_.transpose(nx), F_.transpose(nf), fi
 
 
-class PointNetSetUpConv(nn.Module):
-    """Parameters of ASF/utils/utils.py:250-272."""
+class PointNetSetUpConv(_OwnWeights, nn.Module):
+    """ASF/utils/utils.py:250-315."""
+    _kind = "su"
 
     def __init__(self, nsample, radius, f1_channel, f2_channel, mlp, mlp2, knn=True):
         super().__init__()
@@ -69,10 +104,48 @@ class PointNetSetUpConv(nn.Module):
         for c in mlp2:
             self.mlp2_convs.append(nn.Sequential(nn.Conv1d(last, c, 1, bias=False), nn.BatchNorm1d(c), nn.ReLU()))
             last = c
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, pos1, pos2, feature1, feature2):
+        """pos1 [B,3,N1] dense, pos2 [B,3,N2] sparse, feature1 [B,C1,N1], feature2 [B,C2,N2] -> [B,mlp2[-1],N1]
+        (ASF/utils/utils.py:274-315; eval mode)."""
+        nat.require_device()
+        F_.knn_cache_clear()
+        out = set_upconv_pm(self._own(pos1.device), self.nsample, _pm(pos1), _pm(pos2), _pm(feature1), _pm(feature2))
+        F_.knn_cache_clear()
+        return F_.transpose(out)
 
 
-class PointConvTransFlowV2(nn.Module):
-    """Parameters of ASF/utils/soflow.py:281-346 (bn=False, 3-channel flow head)."""
+class PointWarping(nn.Module):
+    """ASF/utils/soflow.py:1222-1257: pos2 pulled back by the flow interpolated from pos1 + flow1 (no parameters)."""
+
+    @torch.no_grad()
+    def forward(self, pos1, pos2, flow1=None, nsample=None):
+        if flow1 is None:
+            return pos2
+        nat.require_device()
+        F_.knn_cache_clear()
+        out = point_warping_pm(_pm(pos1), _pm(pos2), _pm(flow1), nsample)
+        F_.knn_cache_clear()
+        return F_.transpose(out)
+
+
+class UpsampleFlow(nn.Module):
+    """ASF/utils/soflow.py:1442-1475: normalised inverse-distance interpolation from the sparse level (no parameters)."""
+
+    @torch.no_grad()
+    def forward(self, xyz, sparse_xyz, sparse_flow, k=3):
+        nat.require_device()
+        F_.knn_cache_clear()
+        out = upsample_pm(_pm(xyz), _pm(sparse_xyz), _pm(sparse_flow), k)
+        F_.knn_cache_clear()
+        return F_.transpose(out)
+
+
+class PointConvTransFlowV2(_OwnWeights, nn.Module):
+    """ASF/utils/soflow.py:281-525 (bn=False, 3-channel flow head)."""
+    _kind = "cv"
 
     def __init__(self, nsample, in_channel, sf_channel, mlp, flow_mlp, use_flow=True):
         super().__init__()
@@ -100,15 +173,39 @@ class PointConvTransFlowV2(nn.Module):
             self.flow_mlp_convs.append(_LeakyConv1d(last, c, bias=True))
             last = c
         self.fc = nn.Conv1d(last, 3, 1)
+        self.eval()
+
+    @torch.no_grad()
+    def forward(self, xyz1, xyz2, xyz2w, points1, points2, sf=None, sf_feat=None):
+        """xyz1 [B,3,N1], xyz2 [B,3,N2], xyz2w [B,3,N2] or None, points1 [B,D,N1], points2 [B,D,N2], sf [B,3,N1],
+        sf_feat [B,F,N1] -> (cost_fwd [B,m,N1], cost_bwd [B,m,N2], feats [B,flow_mlp[-1],N1], flow [B,3,N1])
+        (ASF/utils/soflow.py:354-525).  The backward cost has all N2 columns (zeros where the reference's tensor ends)."""
+        nat.require_device()
+        if self.nsample != 16:
+            raise nat.SsfError("PointConvTransFlowV2: the fused kernels are built for nsample == 16 (as in TFlow)")
+        F_.knn_cache_clear()
+        outs = cost_volume_pm(self._own(xyz1.device), _pm(xyz1), _pm(xyz2), None if xyz2w is None else _pm(xyz2w), _pm(points1),
+                              None, _pm(points2), None, sf=None if sf is None else _pm(sf),
+                              sf_feat=None if sf_feat is None else _pm(sf_feat))
+        F_.knn_cache_clear()
+        return tuple(F_.transpose(o) for o in outs)
 
 
 class RefineFlowRegressor(nn.Module):
-    """ASF/TFlowV3_Occlussion.py:41-49: `.cost` holds the cost volume; `.warping` has no parameters."""
+    """ASF/TFlowV3_Occlussion.py:41-62: optional PointWarping, then the cost volume."""
 
-    def __init__(self, nsample, in_channel, feat_channel, mlp, flow_mlp, use_flow=True):
+    def __init__(self, nsample=8, in_channel=128, feat_channel=128, mlp=(128, 128, 128), flow_mlp=(128, 128), use_flow=True):
         super().__init__()
         self.use_flow, self.nsample = use_flow, nsample
-        self.cost = PointConvTransFlowV2(nsample, in_channel, feat_channel, mlp, flow_mlp, use_flow=use_flow)
+        self.cost = PointConvTransFlowV2(nsample, in_channel, feat_channel, list(mlp), list(flow_mlp), use_flow=use_flow)
+        self.warping = PointWarping()
+
+    @torch.no_grad()
+    def forward(self, pc1, pc2, feats1, feats2, wraping_num=5, c_flow=None, flow_feats=None):
+        pc2_warp = None if c_flow is None else self.warping(pc1, pc2, c_flow, wraping_num)
+        if self.use_flow:
+            return self.cost(pc1, pc2, pc2_warp, feats1, feats2, c_flow, flow_feats)
+        return self.cost(pc1, pc2, pc2_warp, feats1, feats2)
 
 
 # ------------------------------------------------------------------------------ weight preparation
@@ -127,6 +224,17 @@ def _kmajor(w2d):
 
 def prepare_weights(state_dict, device):
     """Reference-format state_dict -> dict of K-major, BN-folded fp32 device tensors used by the kernels."""
+    return _prepare(state_dict, device, None)
+
+
+def prepare_block(kind, state_dict, device):
+    """Operands of ONE layer object from its own state_dict: kind in {"sa", "su", "cv"} (PointNetSetAbstraction,
+    PointNetSetUpConv, PointConvTransFlowV2).  Used by the drop-in layer classes' own ``forward``."""
+    sd = {"x." + k: v for k, v in state_dict.items()}
+    return _prepare(sd, device, kind)
+
+
+def _prepare(state_dict, device, only):
     sd = {k[7:] if k.startswith("module.") else k: v.detach().to("cpu") for k, v in state_dict.items()}
     W = {}
     eps = 1e-5
@@ -142,14 +250,15 @@ def prepare_weights(state_dict, device):
         """[Cout, Cin] -> tensor-core weight image (ssf_dense_tc)"""
         return dev(tc.dense_image(w_nk.contiguous()))
 
-    W["pc0"] = dev(_kmajor(w2("point_conv.0.composed_module.0.weight")))
-    W["pc1"] = dev(_kmajor(w2("point_conv.1.composed_module.0.weight")))
-    W["pc1_img"] = img(w2("point_conv.1.composed_module.0.weight"))
-    for name in ("deconv3_2", "deconv2_1", "deconv1_0"):
-        W[name] = dev(_kmajor(w2(name + ".composed_module.0.weight")))
-        W[name + "_img"] = img(w2(name + ".composed_module.0.weight"))
+    if only is None:
+        W["pc0"] = dev(_kmajor(w2("point_conv.0.composed_module.0.weight")))
+        W["pc1"] = dev(_kmajor(w2("point_conv.1.composed_module.0.weight")))
+        W["pc1_img"] = img(w2("point_conv.1.composed_module.0.weight"))
+        for name in ("deconv3_2", "deconv2_1", "deconv1_0"):
+            W[name] = dev(_kmajor(w2(name + ".composed_module.0.weight")))
+            W[name + "_img"] = img(w2(name + ".composed_module.0.weight"))
 
-    for name in ("sa1", "sa2", "sa3", "sa4"):
+    for name in (("sa1", "sa2", "sa3", "sa4") if only is None else (("x",) if only == "sa" else ())):
         layers = []
         i = 0
         while "%s.mlp_convs.%d.weight" % (name, i) in sd:
@@ -163,7 +272,7 @@ def prepare_weights(state_dict, device):
                        W3=dev(_kmajor(layers[2][0])), b3=dev(layers[2][1]), C3=layers[2][0].shape[0], C1=w1.shape[0],
                        Wg_img=img(w1[:, 3:]), W2_img=img(layers[1][0]), W3_img=img(layers[2][0]))
 
-    for name in ("su3", "su2", "su1", "su0"):
+    for name in (("su3", "su2", "su1", "su0") if only is None else (("x",) if only == "su" else ())):
         m1 = []
         i = 0
         while "%s.mlp1_convs.%d.0.weight" % (name, i) in sd:
@@ -183,8 +292,8 @@ def prepare_weights(state_dict, device):
                        M2=dev(_kmajor(m2[1][0])), mb2=dev(m2[1][1]), MC2=m2[1][0].shape[0],
                        Wg_img=img(w1[:, :c2]), W2_img=img(m1[1][0]), M1_img=img(m2[0][0]), M2_img=img(m2[1][0]))
 
-    for name in ("flow3_r", "flow2_r", "flow1_r", "flow0_r"):
-        p = name + ".cost"
+    for name in (("flow3_r", "flow2_r", "flow1_r", "flow0_r") if only is None else (("x",) if only == "cv" else ())):
+        p = name + ".cost" if only is None else name
         wa, ba = w2(p + ".mlp_convs.0.weight"), sd[p + ".mlp_convs.0.bias"].float()
         ww, bw = w2(p + ".mlp_convs2.0.weight"), sd[p + ".mlp_convs2.0.bias"].float()
         m, D = wa.shape[0], wa.shape[1] // 2
@@ -230,7 +339,7 @@ def prepare_weights(state_dict, device):
             i += 1
         d["flow_mlp"] = fm
         W[name] = d
-    return W
+    return W if only is None else W["x"]
 
 
 # ------------------------------------------------------------------------------ point-major forward pieces

@@ -207,3 +207,47 @@ def test_frontend_cuda_graph_replay_equals_eager(setup, golden_dir):
         a = {k: v.clone() for k, v in eager.process(it["pos1"][None], it["pos2"][None], return_flow=True).items()}
         b = graph.process(it["pos1"][None], it["pos2"][None], return_flow=True)
         assert torch.equal(a["mask"], b["mask"]) and torch.equal(a["odom"], b["odom"]) and torch.equal(a["flow"], b["flow"])
+
+
+def _sub_sd(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def test_layer_classes_are_dropins(setup):
+    """B-layer boundary: the layer classes constructed and called exactly as ASF/TFlowV3_Occlussion.py:70-97,113-187 does
+    (reference [B,C,N] layouts, own state_dict), checked against the oracle's restatement of the reference layers."""
+    from ssf_slam_b200 import model as M
+    inter, sd = setup["inter"], setup["sd"]
+    cu = lambda t: t.cuda().contiguous()
+    # PointNetSetAbstraction (sa2)
+    sa = M.PointNetSetAbstraction(npoint=512, radius=2.0, nsample=16, in_channel=64, mlp=[64, 64, 128], group_all=False)
+    sa.load_state_dict(_sub_sd(sd, "sa2."), strict=True)
+    nx, nf, fi = sa(cu(inter["pcs1"][1]), cu(inter["f1"][1]))
+    assert torch.equal(fi.cpu(), inter["fps"][1]) and torch.equal(nx.cpu(), inter["pcs1"][2])
+    assert float((nf.cpu() - inter["f1"][2]).abs().max()) < 2e-5 * max(1.0, float(inter["f1"][2].abs().max()))
+    # PointNetSetUpConv (su3)
+    su = M.PointNetSetUpConv(nsample=16, radius=2.4, f1_channel=256, f2_channel=512, mlp=[256, 256], mlp2=[256, 256])
+    su.load_state_dict(_sub_sd(sd, "su3."), strict=True)
+    want = tp.set_upconv(sd, "su3", 16, inter["pcs1"][3], inter["pcs1"][4], inter["f1"][3], inter["f1"][4])
+    got = su(cu(inter["pcs1"][3]), cu(inter["pcs1"][4]), cu(inter["f1"][3]), cu(inter["f1"][4]))
+    assert float((got.cpu() - want).abs().max()) < 2e-5 * max(1.0, float(want.abs().max()))
+    # RefineFlowRegressor / PointConvTransFlowV2 (flow3_r: no flow input)
+    u1 = want
+    u2 = tp.set_upconv(sd, "su3", 16, inter["pcs2"][3], inter["pcs2"][4], inter["f2"][3], inter["f2"][4])
+    rf = M.RefineFlowRegressor(nsample=16, in_channel=256, feat_channel=0, mlp=[256, 256], flow_mlp=[128, 128], use_flow=False)
+    rf.load_state_dict(_sub_sd(sd, "flow3_r."), strict=True)
+    outs = rf(cu(inter["pcs1"][3]), cu(inter["pcs2"][3]), cu(u1), cu(u2))
+    ref = tp.cost_volume(sd, "flow3_r.cost", 16, False, inter["pcs1"][3], inter["pcs2"][3], None, u1, u2)
+    for n, w_, g_ in zip(("cost_fwd", "cost_bwd", "feats", "flow"), ref, outs):
+        g_ = g_.cpu()
+        w_ = w_ if n != "cost_bwd" else torch.nn.functional.pad(w_, (0, g_.shape[2] - w_.shape[2]))
+        assert g_.shape == w_.shape and float((g_ - w_).abs().max()) < 3e-5 * max(1.0, float(w_.abs().max())), n
+    # UpsampleFlow / PointWarping
+    flow3 = inter["l3"][3]
+    up = M.UpsampleFlow()(cu(inter["pcs1"][2]), cu(inter["pcs1"][3]), cu(flow3), k=5)
+    want_up = tp.upsample_flow(inter["pcs1"][2], inter["pcs1"][3], flow3, k=5)
+    assert float((up.cpu() - want_up).abs().max()) < 1e-5
+    wp = M.PointWarping()(cu(inter["pcs1"][2]), cu(inter["pcs2"][2]), cu(want_up), 5)
+    want_wp = tp.point_warping(inter["pcs1"][2], inter["pcs2"][2], want_up, 5)
+    assert float((wp.cpu() - want_wp).abs().max()) < 1e-5
+    assert M.PointWarping()(cu(inter["pcs1"][2]), cu(inter["pcs2"][2])) is not None   # flow1=None -> pos2 itself

@@ -773,20 +773,37 @@ seg_softmax_sum_kernel(const float* __restrict__ logit, const float* __restrict_
             w_l = expf(lg[r_l] - mx) / den;
         }
         const int nb = min(32, hi - base);
-        for (int t = 0; t < nb; ++t) {
-            const int r = __shfl_sync(0xffffffffu, r_l, t);
-            const float w = __shfl_sync(0xffffffffu, w_l, t);
-            const float* vr = v + (size_t)r * C;
+        // four rows per step: their loads are independent and in flight together (a segment is a short list of random
+        // rows, so a one-row-at-a-time loop is a chain of exposed L2 latencies); accumulation order stays ascending
+        for (int t0 = 0; t0 < nb; t0 += 4) {
+            float wv[4];
+            const float* vr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = min(t0 + u, nb - 1);
+                const int r = __shfl_sync(0xffffffffu, r_l, t);
+                wv[u] = t0 + u < nb ? __shfl_sync(0xffffffffu, w_l, t) : 0.f;
+                vr[u] = v + (size_t)r * C;
+            }
 #pragma unroll
             for (int q = 0; q < MAXV / VEC; ++q) {
                 const int c = (q * 32 + lane) * VEC;
                 if (c < C) {
                     if (VEC == 2) {
-                        const float2 x = __ldg(reinterpret_cast<const float2*>(vr + c));
-                        acc[q * 2] += x.x * w;
-                        acc[q * 2 + 1] += x.y * w;
+                        float2 x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = __ldg(reinterpret_cast<const float2*>(vr[u] + c));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            acc[q * 2] += x[u].x * wv[u];
+                            acc[q * 2 + 1] += x[u].y * wv[u];
+                        }
                     } else {
-                        acc[q] += __ldg(vr + c) * w;
+                        float x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = __ldg(vr[u] + c);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[q] += x[u] * wv[u];
                     }
                 }
             }

@@ -90,3 +90,21 @@ def test_sharding_and_final_gather_gloo_world2():
     assert res[0][1] == list(range(0, 64, 2)) and res[1][1] == list(range(1, 64, 2))
     for r in res:
         assert r[2] == [0.0, 1.0] and r[3] == [0, 1]
+
+
+def test_carla_subsampler_matches_reference_golden():
+    """f-2: our loader/subsampler reproduces the UNMODIFIED reference method's output (golden written by
+    oracle/gen_golden_dataset.py, which calls CARLA3D.subsample_points itself) under the same NumPy seed."""
+    import os
+    from ssf_slam_b200 import dataset
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "carla_subsample.npz"))
+    frame = {k: g[k] for k in ("pos1", "pos2", "ego_flow", "gt", "s_fg_mask", "t_fg_mask")}
+    cases = (("default", 512, {}), ("noseg_rmground", 1024, dict(pre_segfrnt=False, rm_ground=True)),
+             ("small_replace", 1024, dict(pre_segfrnt=True)), ("hybrid", 1024, dict(hybrid_sample=True)))
+    for tag, nb, flags in cases:
+        seq, gt, mask = dataset.load_sequence(frame)
+        np.random.seed(1234)
+        s, t, m = dataset.subsample_points(seq, gt, mask, nb, **flags)
+        for name, got in (("pos1", s[0]), ("pos2", s[1]), ("ego", t[0]), ("gt", t[1]), ("m0", m[0]), ("m1", m[1])):
+            assert np.array_equal(got, g[tag + "_" + name]), (tag, name)
+    assert frame["pos1"].shape == (3000, 3)   # inputs untouched

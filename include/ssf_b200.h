@@ -158,6 +158,14 @@ int ssf_frontend(const float* points, const float* flow, int B, int N, int mode,
 int ssf_tc_gemm_test(const float* X, const float* Whi_img, const float* Wlo_img, int K, int N, int mode, int passes,
                      float* Y, void* stream);
 
+/* ---- next after the path: plane-feature extraction of the back end's first node, src/frameFeature.cpp:45-127
+ * (scan-line id from elevation, stable regrouping per line, 11-tap curvature, greedy selection curvature < plane_min with a
+ * skip of plane_span).  points [B,N,3] -> out [B,N,4] = (x, y, z, intensity = indexInRow + line/100), out_count [B].
+ * n_rows in {16, 64}; the node's parameters are (16: 0.05, 3, rows 0..15) and (64: 0.005, 25, rows 5..58). */
+long long ssf_plane_features_workspace_bytes(int B, int N);
+int ssf_plane_features(const float* points, int B, int N, int n_rows, int row_start, int row_end, float plane_min,
+                       int plane_span, void* ws, float* out, int* out_count, void* stream);
+
 /* tensor-pipe pacing probe (developer tool): cycles for `reps` back-to-back M128 x N x K8 kind::tf32 MMAs, A operand from
  * TMEM (mode 0) or shared memory (mode 1), acc_bufs accumulators round-robin; out[0] = total cycles, out[1] = issue cycles */
 int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long long* out, void* stream);

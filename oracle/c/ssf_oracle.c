@@ -141,3 +141,64 @@ void ssf_oracle_group(const float *feat, const int32_t *idx, int B, int C, int N
         }
     }
 }
+
+/* ---- plane-feature extraction: restatement of src/frameFeature.cpp:45-127 (test infrastructure; parity unpinned: the
+ * node cannot be compiled here -- ROS / PCL absent -- so this follows the source line by line: float/double types of
+ * every sub-expression as C++ would evaluate them with the <cmath> float overloads).
+ * points [N,3]; out [N,4]; returns the number of plane points.  tmp: N ints + N ints + N floats + N ints. */
+int ssf_oracle_plane_features(const float* P, int N, int n_rows, int row_start, int row_end, float plane_min, int plane_span,
+                              float* out) {
+    int* row_of = (int*)malloc(sizeof(int) * (size_t)N);
+    int* cnt = (int*)calloc((size_t)n_rows, sizeof(int));
+    int* off = (int*)calloc((size_t)n_rows + 1, sizeof(int));
+    for (int i = 0; i < N; ++i) {
+        const float x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+        float angle = (float)((double)(atanf(z / sqrtf(x * x + y * y)) * 180) / M_PI);   /* :56 */
+        int id = -1;
+        if (n_rows == 16) {
+            if (angle >= -15 || angle <= 15) id = (int)((angle + 15) / 2 + 0.5);          /* :58-60 */
+        }
+        if (n_rows == 64) {
+            if (angle >= -24.33 || angle <= 2) {                                            /* :63-69 */
+                if (angle >= -8.83) id = (int)((2 - angle) * 3.0 + 0.5);
+                else id = n_rows / 2 + (int)((-8.83 - angle) * 2.0 + 0.5);
+            }
+        }
+        if (angle != angle) id = -1;
+        row_of[i] = (id > -1 && id < n_rows) ? id : -1;
+        if (row_of[i] >= 0) cnt[row_of[i]]++;
+    }
+    for (int r = 0; r < n_rows; ++r) off[r + 1] = off[r] + cnt[r];
+    int* sorted = (int*)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
+    int* fill = (int*)calloc((size_t)n_rows, sizeof(int));
+    for (int i = 0; i < N; ++i)
+        if (row_of[i] >= 0) sorted[off[row_of[i]] + fill[row_of[i]]++] = i;               /* push_back order, :74-82 */
+    float* value = (float*)calloc((size_t)(N > 0 ? N : 1), sizeof(float));
+    for (int r = row_start; r < n_rows - row_end; ++r) {                                    /* :85-108 */
+        const int* s = sorted + off[r];
+        for (int j = 5; j < cnt[r] - 5; ++j) {
+            float d[3];
+            for (int c = 0; c < 3; ++c) {
+#define AT(k) P[3 * s[j + (k)] + c]
+                d[c] = AT(-5) + AT(-4) + AT(-3) + AT(-2) + AT(-1) - 10 * AT(0) + AT(1) + AT(2) + AT(3) + AT(4) + AT(5);
+#undef AT
+            }
+            value[off[r] + j] = (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        }
+    }
+    int n_out = 0;
+    for (int r = row_start; r < n_rows - row_end; ++r) {                                    /* :110-126 */
+        size_t jstart = 0;
+        for (size_t j = 0; j < (size_t)cnt[r]; ++j) {
+            if (j >= jstart && value[off[r] + j] < plane_min) {
+                const int i = sorted[off[r] + j];
+                out[4 * n_out] = P[3 * i]; out[4 * n_out + 1] = P[3 * i + 1]; out[4 * n_out + 2] = P[3 * i + 2];
+                out[4 * n_out + 3] = (float)((int)j + r / 100.0);                          /* :79 */
+                ++n_out;
+                jstart = j + plane_span;
+            }
+        }
+    }
+    free(row_of); free(cnt); free(off); free(sorted); free(fill); free(value);
+    return n_out;
+}

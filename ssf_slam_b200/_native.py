@@ -52,6 +52,8 @@ SIGNATURES = {
     "ssf_dense_tc": ("pp", _I),
     "ssf_dense_args_bytes": ("", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
+    "ssf_plane_features_workspace_bytes": ("ii", _I64),
+    "ssf_plane_features": ("piiiiifipppp", _I),
     "ssf_tc_gemm_test": ("pppiiiipp", _I),
     "ssf_tc_mma_rate": ("iiiipp", _I),
 }

@@ -1,0 +1,50 @@
+"""f-3: plane-feature extraction after src/frameFeature.cpp:45-127.
+CPU: the two oracle restatements (C, Python) agree.  GPU: the kernel equals the C oracle bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import plane_features as opf  # checker only
+
+
+def lidar_cloud(seed, n, n_rows):
+    """Points on scan lines with elevations well inside a line's angular bin (scan-line decisions are then independent
+    of the last ulp of atan), mixed ranges, a few degenerate points (origin, vertical, duplicates)."""
+    rng = np.random.default_rng(seed)
+    if n_rows == 16:
+        ang = (rng.integers(-1, 17, n) * 2 - 15) + rng.uniform(-0.8, 0.8, n)
+    else:
+        k = rng.integers(0, 70, n)
+        ang = np.where(k < 33, 2 - (k + rng.uniform(-0.4, 0.4, n)) / 3.0, -8.83 - ((k - 32) + rng.uniform(-0.4, 0.4, n)) / 2.0)
+    az = np.sort(rng.uniform(-np.pi, np.pi, n))
+    rad = 5 + 40 * rng.random(n) ** 2 + 0.02 * rng.standard_normal(n)
+    wall = rng.random(n) < 0.5
+    rad = np.where(wall, 12.0 / np.maximum(np.abs(np.cos(az)), 0.2), rad)    # a flat wall -> low curvature runs
+    pts = np.stack([rad * np.cos(az), rad * np.sin(az), rad * np.tan(np.deg2rad(ang))], 1).astype(np.float32)
+    pts[::97] = pts[1::97][: len(pts[::97])]      # duplicates
+    pts[5] = 0                                    # origin: angle NaN -> dropped
+    pts[6, :2] = 0                                # vertical: +-90 degrees -> out of range
+    return pts
+
+
+@pytest.mark.parametrize("n_rows,n", [(16, 700), (64, 1500)])
+def test_oracle_restatements_agree(oracle_c, n_rows, n):
+    pts = lidar_cloud(n_rows, n, n_rows)
+    a = opf.plane_features_c(pts, n_rows)
+    b = opf.plane_features_py(pts, n_rows)
+    assert a.shape == b.shape and a.shape[0] > 20
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_rows,B,n", [(16, 3, 8192), (64, 2, 8192), (16, 1, 1000), (64, 1, 16384), (16, 2, 37)])
+def test_plane_features_gpu_equals_oracle(oracle_c, n_rows, B, n):
+    import torch
+    from ssf_slam_b200.plane_features import plane_features
+    clouds = np.stack([lidar_cloud(100 * n_rows + b, n, n_rows) for b in range(B)])
+    out, cnt = plane_features(torch.from_numpy(clouds).cuda(), n_rows)
+    out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+    for b in range(B):
+        want = opf.plane_features_c(clouds[b], n_rows)
+        assert cnt[b] == want.shape[0]
+        assert np.array_equal(out[b, :cnt[b]], want)
+        assert not out[b, cnt[b]:].any()

@@ -15,6 +15,13 @@
 #include "ssf_common.cuh"
 #include <math_constants.h>
 
+#ifdef SSF_CV_TRACE
+__device__ unsigned long long g_knn_stat[4];   // queries, visits, inserts, sweep re-checks
+#define KSTAT(i, n) do { if (lane == 0) atomicAdd(&g_knn_stat[i], (unsigned long long)(n)); } while (0)
+#else
+#define KSTAT(i, n) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int KB_BUILD_T = 1024;
@@ -175,7 +182,9 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
         float list_d = CUDART_INF_F, kth_d = CUDART_INF_F;
         int list_i = 0x7fffffff, kth_i = 0x7fffffff;
         // evaluates block `blk` (lane = point) and merges the survivors into the lane-distributed sorted list
+        KSTAT(0, 1);
         auto visit = [&](int blk) {
+            KSTAT(1, 1);
             const float4 p = __ldg(P + (size_t)blk * 32 + lane);
             const float d = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z);
             const int pi = __float_as_int(p.w);
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
                 const float cd = __shfl_sync(0xffffffffu, d, src);
                 const int ci = __shfl_sync(0xffffffffu, pi, src);
                 if (!key_less(cd, ci, kth_d, kth_i)) continue;   // warp-uniform: the k-th key tightened meanwhile
+                KSTAT(2, 1);
                 const int pos = __popc(__ballot_sync(0xffffffffu, key_less(list_d, list_i, cd, ci)));
                 const float ud = __shfl_up_sync(0xffffffffu, list_d, 1);
                 const int ui = __shfl_up_sync(0xffffffffu, list_i, 1);
@@ -275,6 +285,7 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
                 const int bl = __ffs(m) - 1;
                 m &= m - 1;
                 const float blb = __shfl_sync(0xffffffffu, lb[s], bl);
+                KSTAT(3, 1);
                 if (blb > kth_d) continue;   // warp-uniform
                 visit(s * 32 + bl);
             }
@@ -294,6 +305,14 @@ inline int next_pow2(int v) {
 }
 
 }  // namespace
+
+#ifdef SSF_CV_TRACE
+extern "C" int ssf_knn_stat_read(unsigned long long* out, int reset) {
+    if (cudaMemcpyFromSymbol(out, g_knn_stat, sizeof(unsigned long long) * 4) != cudaSuccess) return 2;
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_knn_stat, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // floats of workspace for B reference clouds of Nr points
 extern "C" long long ssf_knn_blocks_workspace_floats(int B, int Nr) {

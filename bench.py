@@ -198,7 +198,7 @@ def point_op_rooflines(B, N, dev):
         lambda: pu.grouping_operation(feat96, idx16))
     hbm("three_interpolate[C=96,n=%d]" % N, B * (4.0 * 3 * N * 2 + 4.0 * C * N * 3 + 4.0 * C * N), B * (4.0 * 3 * N * 2 + 8.0 * C * N),
         lambda: pu.three_interpolate(feat96, idx3, w3))
-    hbm("gather_operation[C=96,M=%d]" % M, B * (4.0 * M + 8.0 * C * M), B * (4.0 * M + 4.0 * C * N + 4.0 * C * M),
+    hbm("gather_operation[C=96,M=%d]" % M, B * (4.0 * M + 8.0 * C * M), B * (4.0 * M + 8.0 * C * M),
         lambda: pu.gather_operation(feat96, fps_idx))
     rate("furthest_point_sample[N=%d,n=%d]" % (N, M), B * float(N) * M, "G point-updates/s", lambda: pu.furthest_point_sample(xyz, M))
     rate("knn[k=16,%dx%d]" % (N, N), B * float(N) * N, "G pair-evaluations/s (brute-force equivalent)", lambda: pu.knn(16, xyz, xyz))

@@ -140,8 +140,6 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
     }
 }
 
-__device__ __forceinline__ bool key_less(float d, int i, float kd, int ki) { return d < kd || (d == kd && i < ki); }
-
 template <int NBL>
 __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
                                                                 const float* __restrict__ ws, int Nq, int npad, int nblk,
@@ -179,36 +177,30 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
                 lb[s] = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
             }
         }
-        float list_d = CUDART_INF_F, kth_d = CUDART_INF_F;
-        int list_i = 0x7fffffff, kth_i = 0x7fffffff;
+        // (distance, index) packed into one 64-bit key: distances are non-negative, so their bit patterns order like the
+        // values and an unsigned 64-bit compare IS the lexicographic (distance, index) order of the specification
+        unsigned long long list_k = 0x7f8000007fffffffull, kth = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+        float kth_d = CUDART_INF_F;
+        auto pack = [](float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; };
         // evaluates block `blk` (lane = point) and merges the survivors into the lane-distributed sorted list
         KSTAT(0, 1);
         auto visit = [&](int blk) {
             KSTAT(1, 1);
             const float4 p = __ldg(P + (size_t)blk * 32 + lane);
-            const float d = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z);
-            const int pi = __float_as_int(p.w);
-            unsigned mask = __ballot_sync(0xffffffffu, key_less(d, pi, kth_d, kth_i));
+            const unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+            unsigned mask = __ballot_sync(0xffffffffu, key < kth);
             while (mask) {
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const float cd = __shfl_sync(0xffffffffu, d, src);
-                const int ci = __shfl_sync(0xffffffffu, pi, src);
-                if (!key_less(cd, ci, kth_d, kth_i)) continue;   // warp-uniform: the k-th key tightened meanwhile
+                const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
+                if (ck >= kth) continue;   // warp-uniform: the k-th key tightened meanwhile
                 KSTAT(2, 1);
-                const int pos = __popc(__ballot_sync(0xffffffffu, key_less(list_d, list_i, cd, ci)));
-                const float ud = __shfl_up_sync(0xffffffffu, list_d, 1);
-                const int ui = __shfl_up_sync(0xffffffffu, list_i, 1);
-                if (lane == pos) {
-                    list_d = cd;
-                    list_i = ci;
-                } else if (lane > pos) {
-                    list_d = ud;
-                    list_i = ui;
-                }
-                kth_d = __shfl_sync(0xffffffffu, list_d, k - 1);
-                kth_i = __shfl_sync(0xffffffffu, list_i, k - 1);
+                const int pos = __popc(__ballot_sync(0xffffffffu, list_k < ck));
+                const unsigned long long uk = __shfl_up_sync(0xffffffffu, list_k, 1);
+                list_k = lane == pos ? ck : (lane > pos ? uk : list_k);
+                kth = __shfl_sync(0xffffffffu, list_k, k - 1);
             }
+            kth_d = __uint_as_float((unsigned)(kth >> 32));
         };
         // warp-wide argmin of the remaining bounds; marks the winner visited.  Returns -1 when nothing is left.
         auto pop_nearest = [&](float& best_out) -> int {
@@ -242,25 +234,19 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
             float best;
             const int blk = pop_nearest(best);   // >= 0: there is at least one block
             const float4 p = __ldg(P + (size_t)blk * 32 + lane);
-            float d = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z);
-            int pi = __float_as_int(p.w);
+            unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
 #pragma unroll
             for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
                 for (int j = kk >> 1; j > 0; j >>= 1) {
-                    const float od = __shfl_xor_sync(0xffffffffu, d, j);
-                    const int oi = __shfl_xor_sync(0xffffffffu, pi, j);
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
                     const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
-                    if (take_min == key_less(od, oi, d, pi)) {
-                        d = od;
-                        pi = oi;
-                    }
+                    if (take_min == (ok < key)) key = ok;
                 }
             }
-            list_d = d;
-            list_i = pi;
-            kth_d = __shfl_sync(0xffffffffu, list_d, k - 1);
-            kth_i = __shfl_sync(0xffffffffu, list_i, k - 1);
+            list_k = key;
+            kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+            kth_d = __uint_as_float((unsigned)(kth >> 32));
         }
         // 2) a few nearest-first visits tighten the k-th distance quickly
 #pragma unroll 1
@@ -292,8 +278,8 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
         }
         if (lane < k) {
             const size_t o = ((size_t)b * Nq + qi) * k + lane;
-            idx[o] = list_i;
-            if (dist != nullptr) dist[o] = __fsqrt_rn(list_d);
+            idx[o] = (int)(unsigned)(list_k & 0xffffffffull);
+            if (dist != nullptr) dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(list_k >> 32)));
         }
     }
 }

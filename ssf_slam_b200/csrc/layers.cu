@@ -14,7 +14,11 @@
 //    weightnet1, forward cost (ASF/utils/soflow.py:397-469,486); emits the warped-branch rows for the
 //    deterministic segmented softmax/sum that forms the backward cost (:471-481).
 //
-// This file is the SIMT fp32 (FFMA) realisation: bit-faithful fp32 accumulation, used for all widths.
+// This file holds the SIMT fp32 (FFMA) realisations.  The product path runs the dense layers on tcgen05 (dense_tc.cu,
+// cost_volume_tc.cu); these kernels remain (a) for the three layers tensor cores cannot take (3 input or 3 output
+// channels: point_conv[0], fc), (b) as the in-repo fp32 reference the tensor-core kernels are tested against
+// (functional.USE_TC = False), and they carry the small point-major helpers (transpose, row gather, interpolation,
+// segmented softmax-sum).
 #include "ssf_common.cuh"
 
 constexpr int L_T = 256;   // threads per CTA in the fused kernels

@@ -32,9 +32,20 @@ from ssf_slam_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def gen_tflow(n_points, data_seed, weight_seed=0):
+def gen_tflow(n_points, data_seed, weight_seed=0, flow_channels=3):
+    """flow_channels=4: the reference with its source flag ``add_Seg_after_FLow`` (utils/datasets/carla.py:9, imported by
+    name into utils/soflow.py:8) switched on for the duration of the call -- 4-channel flow heads."""
     TFlow = import_reference_tflow()
-    sd = tflow_port.random_init_state_dict(weight_seed)
+    import utils.soflow as ref_soflow  # the reference module whose global the classes read
+    ref_soflow.add_Seg_after_FLow = flow_channels == 4
+    try:
+        _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels)
+    finally:
+        ref_soflow.add_Seg_after_FLow = False
+
+
+def _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels):
+    sd = tflow_port.random_init_state_dict(weight_seed, flow_channels)
     net = TFlow().eval()
     net.load_state_dict(sd, strict=True)
     item = synth.make_pair(data_seed, n_points)
@@ -47,11 +58,12 @@ def gen_tflow(n_points, data_seed, weight_seed=0):
         assert torch.equal(a, b), "oracle port deviates from the reference"
     for a, b in zip(fps, pfps):
         assert torch.equal(a, b), "oracle port FPS deviates from the reference"
-    np.savez_compressed(os.path.join(OUT, "tflow_n%d.npz" % n_points), pos1=item["pos1"], pos2=item["pos2"],
+    name = "tflow_n%d.npz" % n_points if flow_channels == 3 else "tflow_seg4_n%d.npz" % n_points
+    np.savez_compressed(os.path.join(OUT, name), pos1=item["pos1"], pos2=item["pos2"],
                         flow0=flows[0][0].numpy(), flow1=flows[1][0].numpy(), flow2=flows[2][0].numpy(),
                         flow3=flows[3][0].numpy(), fps1=fps[0][0].numpy(), fps2=fps[1][0].numpy(), fps3=fps[2][0].numpy(),
-                        weight_seed=weight_seed, data_seed=data_seed)
-    print("tflow_n%d: reference == port (bit-exact); |flow|max %.4f" % (n_points, float(flows[0].abs().max())))
+                        weight_seed=weight_seed, data_seed=data_seed, flow_channels=flow_channels)
+    print("%s: reference == port (bit-exact); |flow|max %.4f" % (name, float(flows[0].abs().max())))
 
 
 def _reference_solve_rt():
@@ -131,3 +143,4 @@ if __name__ == "__main__":
     gen_masker()
     gen_tflow(2048, data_seed=42)
     gen_tflow(8192, data_seed=0)
+    gen_tflow(2048, data_seed=43, flow_channels=4)

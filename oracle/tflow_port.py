@@ -111,13 +111,13 @@ def point_warping(pos1, pos2, flow1, nsample):
     """PointWarping.forward, ASF/utils/soflow.py:1223-1257 (positions clamped to +-10 m)."""
     if flow1 is None:
         return pos2
-    moved = pos1 + flow1
+    moved = pos1 + flow1[:, 0:3, :]   # 4-channel flows (add_Seg_after_FLow, soflow.py:1228) move by their first three
     if nsample is None:
         _, idx = ops.three_nn(_t(pos2), _t(moved))
     else:
         _, idx = ops.knn(nsample, _t(pos2), _t(moved))
     flow2 = _inv_dist_interp(pos2, moved, flow1, idx)
-    return (pos2 - flow2).clamp(-10.0, 10.0)
+    return (pos2 - flow2[:, 0:3, :]).clamp(-10.0, 10.0)   # soflow.py:1252-1257
 
 
 def _weightnet(sd, p, x):
@@ -147,7 +147,7 @@ def cost_volume(sd, prefix, nsample, use_flow, xyz1, xyz2, xyz2w, points1, point
 
     if sf is not None and use_flow:
         sf_t = _t(sf)
-        _, idx = ops.knn(S, x1 + sf_t, x2)
+        _, idx = ops.knn(S, x1 + sf_t[:, :, 0:3], x2)   # soflow.py:386-389 (identity slice for 3-channel flows)
     else:
         if sf is not None:
             sf_t = _t(sf)

@@ -118,7 +118,8 @@ class SceneFlowFrontEnd:
 
     def _run(self, x1, x2, ts, ti, n_inst):
         flows, _ = self.net.forward_pm(x1, x2)
-        mask, odom = F_.frontend(x1, flows[0], mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
+        flow = flows[0] if flows[0].shape[-1] == 3 else flows[0][..., :3].contiguous()   # 4-channel heads: xyz flow only
+        mask, odom = F_.frontend(x1, flow, mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
         return flows[0], mask, odom
 
     def _graph_for(self, slot, B, N, seg, n_inst):

@@ -147,7 +147,7 @@ class PointConvTransFlowV2(_OwnWeights, nn.Module):
     """ASF/utils/soflow.py:281-525 (bn=False, 3-channel flow head)."""
     _kind = "cv"
 
-    def __init__(self, nsample, in_channel, sf_channel, mlp, flow_mlp, use_flow=True):
+    def __init__(self, nsample, in_channel, sf_channel, mlp, flow_mlp, use_flow=True, flow_channels=3):
         super().__init__()
         self.nsample, self.use_flow = nsample, use_flow
         self.in_channel, self.sf_channel, self.mlp, self.flow_mlp = in_channel, sf_channel, list(mlp), list(flow_mlp)
@@ -172,7 +172,7 @@ class PointConvTransFlowV2(_OwnWeights, nn.Module):
         for c in flow_mlp:
             self.flow_mlp_convs.append(_LeakyConv1d(last, c, bias=True))
             last = c
-        self.fc = nn.Conv1d(last, 3, 1)
+        self.fc = nn.Conv1d(last, flow_channels, 1)   # 4 with the reference's add_Seg_after_FLow flag (soflow.py:343-346)
         self.eval()
 
     @torch.no_grad()
@@ -194,10 +194,12 @@ class PointConvTransFlowV2(_OwnWeights, nn.Module):
 class RefineFlowRegressor(nn.Module):
     """ASF/TFlowV3_Occlussion.py:41-62: optional PointWarping, then the cost volume."""
 
-    def __init__(self, nsample=8, in_channel=128, feat_channel=128, mlp=(128, 128, 128), flow_mlp=(128, 128), use_flow=True):
+    def __init__(self, nsample=8, in_channel=128, feat_channel=128, mlp=(128, 128, 128), flow_mlp=(128, 128), use_flow=True,
+                 flow_channels=3):
         super().__init__()
         self.use_flow, self.nsample = use_flow, nsample
-        self.cost = PointConvTransFlowV2(nsample, in_channel, feat_channel, list(mlp), list(flow_mlp), use_flow=use_flow)
+        self.cost = PointConvTransFlowV2(nsample, in_channel, feat_channel, list(mlp), list(flow_mlp), use_flow=use_flow,
+                                         flow_channels=flow_channels)
         self.warping = PointWarping()
 
     @torch.no_grad()
@@ -398,6 +400,8 @@ def upsample_pm(xyz, sparse_xyz, sparse_val, k=3, idx=None):
 
 def point_warping_pm(pos1, pos2, flow1, k):
     """PointWarping: pos2 pulled back by the flow interpolated from pos1 + flow1 (positions clamped to +-10 m)."""
+    if flow1.shape[-1] != 3:   # add_Seg_after_FLow: the 4th channel (segmentation logit) does not move points (soflow.py:1228,1252)
+        flow1 = flow1[..., :3].contiguous()
     moved = pos1 + flow1  # one rounded fp32 add per coordinate, as `pos1 + flow1` at soflow.py:1231 (glue, 3 floats/point)
     idx = F_.knn_idx(3 if k is None else k, pos2, moved)
     return F_.interpolate(pos2, moved, flow1, idx, mode=1, clampv=10.0)
@@ -436,7 +440,8 @@ def cost_volume_pm(w, xyz1, xyz2, xyz2w, f1a, f1b, f2a, f2b, sf=None, sf_feat=No
     N2 = xyz2.shape[1]
     ca = f1a.shape[-1]
     tcp = _tc()
-    idx = F_.knn_idx(16, xyz1, xyz2, offset=sf)
+    sf3 = sf if sf is None or sf.shape[-1] == 3 else sf[..., :3].contiguous()   # soflow.py:386-389
+    idx = F_.knn_idx(16, xyz1, xyz2, offset=sf3)
     idxw = F_.knn_idx(16, xyz1, xyz2 if xyz2w is None else xyz2w)
     if tcp:
         Hab = F_.dense_tc(w["Hab_img"], 2 * m, D, x1=f1a, x2=f1b, bias=w["bab"])
@@ -473,7 +478,7 @@ def cost_volume_pm(w, xyz1, xyz2, xyz2w, f1a, f1b, f2a, f2b, sf=None, sf_feat=No
         x = F_.group_mlp_max(G4, idx, xyz2, xyz1, w["W4d"], None, w["W42"], w["b42"], m, H=Hp, act=ACT_LEAKY)
         for Wt, b, c, im in w["flow_mlp"]:
             x = F_.linear(x, Wt, c, bias=b, act=ACT_LEAKY)
-    flow = F_.linear(x, w["fc"], 3, bias=w["fcb"], clamp1=50.0, add=sf, clamp2=50.0)
+    flow = F_.linear(x, w["fc"], w["fc"].shape[1], bias=w["fcb"], clamp1=50.0, add=sf, clamp2=50.0)
     return cost_fwd, cost_bwd, x, flow
 
 
@@ -484,21 +489,24 @@ class TFlow(nn.Module):
 
     SA = (("sa1", 2048, 16), ("sa2", 512, 16), ("sa3", 256, 16), ("sa4", 128, 8))
 
-    def __init__(self, npoint=8192):
+    def __init__(self, npoint=8192, add_seg_after_flow=False):
+        """``add_seg_after_flow`` is the reference's source-level flag ``add_Seg_after_FLow`` (utils/datasets/carla.py:9):
+        4-channel flow heads whose last channel is a segmentation logit; shipped default False."""
         super().__init__()
+        fc_ch = 4 if add_seg_after_flow else 3
         self.point_conv = nn.Sequential(_LeakyConv1d(3, 32, bias=False), _LeakyConv1d(32, 32, bias=False))
         self.sa1 = PointNetSetAbstraction(2048, 0.5, 16, 32, [32, 32, 64])
         self.sa2 = PointNetSetAbstraction(512, 2.0, 16, 64, [64, 64, 128])
         self.sa3 = PointNetSetAbstraction(256, 4.0, 16, 128, [128, 128, 256])
         self.sa4 = PointNetSetAbstraction(128, 8.0, 8, 256, [256, 256, 512])
         self.su3 = PointNetSetUpConv(16, 2.4, 256, 512, [256, 256], [256, 256])
-        self.flow3_r = RefineFlowRegressor(16, 256, 0, [256, 256], [128, 128], use_flow=False)
+        self.flow3_r = RefineFlowRegressor(16, 256, 0, [256, 256], [128, 128], use_flow=False, flow_channels=fc_ch)
         self.su2 = PointNetSetUpConv(16, 2.4, 128, 256, [128, 128], [128, 128])
-        self.flow2_r = RefineFlowRegressor(16, 128 + 64, 128, [128, 128], [128, 128])
+        self.flow2_r = RefineFlowRegressor(16, 128 + 64, 128, [128, 128], [128, 128], flow_channels=fc_ch)
         self.su1 = PointNetSetUpConv(16, 2.4, 64, 128, [64, 64], [64, 64])
-        self.flow1_r = RefineFlowRegressor(16, 64 + 32, 128, [64, 64], [64, 64])
+        self.flow1_r = RefineFlowRegressor(16, 64 + 32, 128, [64, 64], [64, 64], flow_channels=fc_ch)
         self.su0 = PointNetSetUpConv(16, 2.4, 32, 64, [64, 64], [64, 64])
-        self.flow0_r = RefineFlowRegressor(16, 64 + 32, 64, [64, 64], [64, 64])
+        self.flow0_r = RefineFlowRegressor(16, 64 + 32, 64, [64, 64], [64, 64], flow_channels=fc_ch)
         self.deconv3_2 = _LeakyConv1d(256, 64, bias=False)
         self.deconv2_1 = _LeakyConv1d(128, 32, bias=False)
         self.deconv1_0 = _LeakyConv1d(64, 32, bias=False)

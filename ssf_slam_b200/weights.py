@@ -8,9 +8,10 @@ reference in oracle/gen_golden.py).  BatchNorm running statistics are non-trivia
 import torch
 
 
-def random_init_state_dict(seed=0):
+def random_init_state_dict(seed=0, flow_channels=3):
     """State dict with the reference's key names and shapes, filled deterministically WITHOUT the
-    reference (for the GPU box).  NOT the reference's init distribution draw-for-draw: goldens that
+    reference (for the GPU box).  ``flow_channels=4`` gives the ``add_Seg_after_FLow=True`` variant's 4-channel flow
+    heads (ASF/utils/soflow.py:343-346).  NOT the reference's init distribution draw-for-draw: goldens that
     must match the reference use the state_dict saved by oracle/gen_golden.py instead."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
@@ -76,7 +77,7 @@ def random_init_state_dict(seed=0):
         for i, c in enumerate(fmlp):
             conv("%s.flow_mlp_convs.%d.composed_module.0" % (p, i), c, last, 1, True)
             last = c
-        conv(p + ".fc", 3, last, 1, True)
+        conv(p + ".fc", flow_channels, last, 1, True)
     conv("deconv3_2.composed_module.0", 64, 256, 1, False)
     conv("deconv2_1.composed_module.0", 32, 128, 1, False)
     conv("deconv1_0.composed_module.0", 32, 64, 1, False)

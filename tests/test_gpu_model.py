@@ -251,3 +251,23 @@ def test_layer_classes_are_dropins(setup):
     want_wp = tp.point_warping(inter["pcs1"][2], inter["pcs2"][2], want_up, 5)
     assert float((wp.cpu() - want_wp).abs().max()) < 1e-5
     assert M.PointWarping()(cu(inter["pcs1"][2]), cu(inter["pcs2"][2])) is not None   # flow1=None -> pos2 itself
+
+
+def test_tflow_four_channel_flow_heads_vs_reference_golden(golden_dir):
+    """f-4: the reference's add_Seg_after_FLow = True variant (4-channel flow heads; golden written by the unmodified
+    reference with its flag switched on): FPS indices exact, all four flow levels within 1e-4."""
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    g = np.load(os.path.join(golden_dir, "tflow_seg4_n2048.npz"))
+    net = TFlow(add_seg_after_flow=True)
+    net.load_state_dict(tp.random_init_state_dict(int(g["weight_seed"]), 4), strict=True)
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0).cuda()
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0).cuda()
+    flows, fps = net(pc1, pc2)
+    for i in range(3):
+        assert np.array_equal(fps[i][0].cpu().numpy(), g["fps%d" % (i + 1)])
+    errs = [float(np.abs(flows[i][0].cpu().numpy() - g["flow%d" % i]).max()) for i in range(4)]
+    print("4-channel flow max-abs error per level:", errs)
+    assert flows[0].shape == (1, 4, 2048) and max(errs) <= FLOW_TOL
+    out = SceneFlowFrontEnd(net, tau=0.10).process(g["pos1"][None], g["pos2"][None], return_flow=True)
+    assert out["flow"].shape == (1, 2048, 4) and out["mask"].shape == (1, 2048)

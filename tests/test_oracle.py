@@ -94,10 +94,12 @@ def test_masker_degenerate_inputs():
     assert np.allclose(out["R"], np.eye(3)) and out["mask"].tolist() == [0, 0]
 
 
-@pytest.mark.parametrize("n", [2048])
-def test_tflow_port_matches_reference_golden(golden_dir, oracle_c, n):
-    g = np.load(os.path.join(golden_dir, "tflow_n%d.npz" % n))
-    sd = tflow_port.random_init_state_dict(int(g["weight_seed"]))
+@pytest.mark.parametrize("n,name,ch", [(2048, "tflow_n2048.npz", 3), (2048, "tflow_seg4_n2048.npz", 4)])
+def test_tflow_port_matches_reference_golden(golden_dir, oracle_c, n, name, ch):
+    """3-channel (shipped) and 4-channel (reference flag add_Seg_after_FLow = True) goldens, both written by
+    the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, name))
+    sd = tflow_port.random_init_state_dict(int(g["weight_seed"]), ch)
     pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0)
     pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0)
     flows, fps = tflow_port.tflow_forward(sd, pc1, pc2)
@@ -105,4 +107,4 @@ def test_tflow_port_matches_reference_golden(golden_dir, oracle_c, n):
         assert np.array_equal(fps[i][0].numpy(), g["fps%d" % (i + 1)])
     for i in range(4):
         # bit-exact in the build container; allow for a different CPU's MKL/oneDNN code path elsewhere
-        assert np.abs(flows[i][0].numpy() - g["flow%d" % i]).max() <= 2e-5
+        assert flows[i].shape[1] == ch and np.abs(flows[i][0].numpy() - g["flow%d" % i]).max() <= 2e-5

@@ -40,6 +40,10 @@ typedef struct ssf_dense_args {
 extern "C" {
 #endif
 int ssf_dense_tc(const ssf_dense_args* args, void* stream);
+/* Layers with N <= 64 and a small weight image run a light kernel variant (288 threads, 256 TMEM columns, two CTAs per SM)
+ * by default; ssf_dense_set_variant(0) forces the one-CTA-per-SM variant everywhere (results are bit-identical).  Returns
+ * the previous setting. */
+int ssf_dense_set_variant(int light);
 int ssf_dense_args_bytes(void);   /* sizeof(ssf_dense_args) as compiled, for binding self-checks */
 #ifdef __cplusplus
 }

@@ -51,6 +51,7 @@ SIGNATURES = {
     "ssf_softmax_pool": ("ppiiippp", _I),
     "ssf_dense_tc": ("pp", _I),
     "ssf_dense_args_bytes": ("", _I),
+    "ssf_dense_set_variant": ("i", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
     "ssf_plane_features_workspace_bytes": ("ii", _I64),
     "ssf_plane_features": ("piiiiifipppp", _I),

@@ -20,6 +20,7 @@
 //                    fits in shared memory keep it resident for the whole kernel; wider ones stream it through a ring.
 // The accumulator is double buffered in TMEM when 2 N + 256 <= 512 columns, so the epilogue of one tile overlaps the
 // MMAs of the next.
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "ssf_dense.h"
 
@@ -27,8 +28,10 @@ namespace {
 
 constexpr int KC = 32;                    // K chunk
 constexpr int AS = 4;                     // TMEM A stages (64 columns each: hi | lo)
-constexpr int DT_THREADS = 448;
+constexpr int DT_THREADS = 448;           // heavy variant: 2 producer warpgroups, 1 CTA per SM
+constexpr int DT_THREADS_LIGHT = 288;     // light variant: 1 producer warpgroup, 2 CTAs per SM (small layers)
 constexpr int W_SMEM_MAX = 160 * 1024;    // bytes of shared memory for weight images
+constexpr int LIGHT_SMEM_MAX = 112 * 1024; // per-CTA shared memory of the light variant (two CTAs per SM)
 constexpr int STG_LD = KC + 4;            // row stride (floats) of a producer warp's transpose tile
 
 struct DenseCfg {
@@ -74,7 +77,16 @@ struct RowCtx {
     float qx, qy, qz; // pos_q[pt]
 };
 
-__global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
+// NPROD = 2: the heavy variant (448 threads, all 512 TMEM columns, one CTA per SM).  NPROD = 1: the light variant for
+// layers whose weight image is small (320 threads, 256 TMEM columns, <= 110 KB shared memory -> two CTAs per SM, i.e. two
+// independent tile pipelines and 20 warps per SM instead of 14; these kernels are bound by warps in flight).
+template <int NPROD>
+__global__ void __launch_bounds__(NPROD == 2 ? DT_THREADS : DT_THREADS_LIGHT, NPROD == 2 ? 1 : 2)
+dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
+    constexpr int NTHR = NPROD == 2 ? DT_THREADS : DT_THREADS_LIGHT;
+    constexpr int W_EPI = 4 * NPROD;          // first epilogue warp
+    constexpr int W_MMA = W_EPI + 4, W_TMA = NPROD == 2 ? W_EPI + 5 : W_EPI + 4;   // light: resident weights, the MMA warp fetches them
+    constexpr uint32_t TCOLS = NPROD == 2 ? 512 : 256;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Nt = cfg.Nt, nk = cfg.nk;
     const int n0 = blockIdx.y * 256;                       // first output column of this CTA
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
     float* sStage = reinterpret_cast<float*>(bars + 46);   // [8 producer warps][32 rows][STG_LD]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 12) tc_alloc(tmem_slot, 512);
+    if (warp == W_MMA) tc_alloc(tmem_slot, TCOLS);
     if (tid == 0) {
         for (int i = 0; i < cfg.nstage; ++i) {
             ssf_mbar_init(&w_full[i], 1);
@@ -113,11 +125,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
         }
         ssf_mbar_fence_init();
     }
-    for (int i = tid; i < a.K; i += DT_THREADS) {
+    for (int i = tid; i < a.K; i += NTHR) {
         sB1[i] = a.b1 ? __ldg(a.b1 + i) : 0.f;
         for (int c = 0; c < 3; ++c) sWd1[c * a.K + i] = a.Wd1 ? __ldg(a.Wd1 + c * a.K + i) : 0.f;
     }
-    for (int i = tid; i < Nt; i += DT_THREADS) {
+    for (int i = tid; i < Nt; i += NTHR) {
         sBias[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
         for (int c = 0; c < 3; ++c) sWd2[c * Nt + i] = a.Wd2 ? __ldg(a.Wd2 + c * a.N + n0 + i) : 0.f;
         sWvec[i] = a.wvec ? __ldg(a.wvec + n0 + i) : 0.f;
@@ -129,27 +141,32 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
     const uint32_t a_col0 = (uint32_t)(cfg.nd * Nt);
     const int n_my = ((int)blockIdx.x < cfg.n_tiles) ? (cfg.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp == 13) {
-        if (lane == 0) {   // ---- weight producer
-            const uint8_t* wsrc = static_cast<const uint8_t*>(a.wimg) + (size_t)blockIdx.y * nk * wchunk;
-            if (cfg.resident) {
-                if (n_my > 0)
-                    for (int kc = 0; kc < nk; ++kc) {
-                        ssf_mbar_expect_tx(&w_full[kc], wchunk);
-                        ssf_bulk_g2s(sW + (size_t)kc * wchunk, wsrc + (size_t)kc * wchunk, wchunk, &w_full[kc]);
-                    }
-            } else {
-                const int total = n_my * nk;
-                for (int g = 0; g < total; ++g) {
-                    const int st = g % cfg.nstage;
-                    if (g >= cfg.nstage) ssf_mbar_wait(&w_empty[st], (uint32_t)((g / cfg.nstage - 1) & 1));
-                    ssf_mbar_expect_tx(&w_full[st], wchunk);
-                    ssf_bulk_g2s(sW + (size_t)st * wchunk, wsrc + (size_t)(g % nk) * wchunk, wchunk, &w_full[st]);
+    auto produce_weights = [&]() {   // ---- weight producer (one thread)
+        const uint8_t* wsrc = static_cast<const uint8_t*>(a.wimg) + (size_t)blockIdx.y * nk * wchunk;
+        if (cfg.resident) {
+            if (n_my > 0)
+                for (int kc = 0; kc < nk; ++kc) {
+                    ssf_mbar_expect_tx(&w_full[kc], wchunk);
+                    ssf_bulk_g2s(sW + (size_t)kc * wchunk, wsrc + (size_t)kc * wchunk, wchunk, &w_full[kc]);
                 }
+        } else {
+            const int total = n_my * nk;
+            for (int g = 0; g < total; ++g) {
+                const int st = g % cfg.nstage;
+                if (g >= cfg.nstage) ssf_mbar_wait(&w_empty[st], (uint32_t)((g / cfg.nstage - 1) & 1));
+                ssf_mbar_expect_tx(&w_full[st], wchunk);
+                ssf_bulk_g2s(sW + (size_t)st * wchunk, wsrc + (size_t)(g % nk) * wchunk, wchunk, &w_full[st]);
             }
         }
+    };
+    if (NPROD == 2 && warp == W_TMA) {
+        if (lane == 0) produce_weights();
         __syncwarp();
-    } else if (warp == 12) {
+    } else if (warp == W_MMA) {
+        if (NPROD == 1) {
+            if (lane == 0) produce_weights();
+            __syncwarp();
+        }
         {   // ---- MMA issuer: warp-uniform control flow, one elected lane executes the tcgen05 instructions
             const bool leader = tc_elect_one();
             const uint32_t idesc = tc_idesc_tf32(128, Nt);
@@ -164,8 +181,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
                 const uint32_t d_tmem = tmem + (uint32_t)(db * Nt);
                 for (int kc = 0; kc < nk; ++kc) {
                     const int g = it * nk + kc;
-                    const int j = (it >> 1) * nk + kc;                // chunk count of the producing warpgroup
-                    const int ws = cfg.resident ? kc : g % cfg.nstage, as = (it & 1) * 2 + (j & 1);
+                    const int j = (it / NPROD) * nk + kc;             // chunk count of the producing warpgroup
+                    const int ws = cfg.resident ? kc : g % cfg.nstage, as = (it % NPROD) * 2 + (j & 1);
                     if (cfg.resident) {
                         if (it == 0) ssf_mbar_wait(&w_full[ws], 0);
                     } else {
@@ -195,7 +212,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
             }
         }
         __syncwarp();
-    } else if (warp < 8) {
+    } else if (warp < W_EPI) {
         // ---- A producers: warpgroup wg takes tiles it = wg, wg + 2, ...
         const int wg = warp >> 2;
         const int r = tid & 127;
@@ -265,17 +282,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
             float v[4][8];
             float4 vn[8];
             nxt = make_ctx(wg, load_idx(wg));
-            idx2 = load_idx(wg + 2);
+            idx2 = load_idx(wg + NPROD);
             issue_loads(nxt, 0, vn);
-            for (int it = wg; it < n_my; it += 2) {
+            for (int it = wg; it < n_my; it += NPROD) {
                 cur = nxt;
-                nxt = make_ctx(it + 2, idx2);       // positions of the next tile: in flight while this tile is processed
-                idx2 = load_idx(it + 4);
+                nxt = make_ctx(it + NPROD, idx2);   // positions of the next tile: in flight while this tile is processed
+                idx2 = load_idx(it + 2 * NPROD);
                 const float dx = cur.px - cur.qx, dy = cur.py - cur.qy, dz = cur.pz - cur.qz;
                 for (int kc = 0; kc < nk; ++kc) {
                     transpose_in(vn, v);
                     if (kc + 1 < nk) issue_loads(cur, kc + 1, vn);
-                    else if (it + 2 < n_my) issue_loads(nxt, 0, vn);
+                    else if (it + NPROD < n_my) issue_loads(nxt, 0, vn);
                     const int k0 = kc * KC;
                     if (a.a_mode == 1) {
                         if (a.H != nullptr) {
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
                     }
                     // each warpgroup owns two of the four A stages and waits on them strictly in order (an mbarrier
                     // parity wait must never run more than one phase ahead of the barrier)
-                    const int j = (it >> 1) * nk + kc, as = wg * 2 + (j & 1);
+                    const int j = (it / NPROD) * nk + kc, as = wg * 2 + (j & 1);
                     if (j >= 2) {
                         ssf_mbar_wait(&a_empty[as], (uint32_t)(((j >> 1) - 1) & 1));
                         tc_fence_after();
@@ -431,10 +448,24 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dense_tc_kernel(ssf_dense_args 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tc_dealloc(tmem, 512);
+    if (warp == W_MMA) tc_dealloc(tmem, TCOLS);
 }
 
 }  // namespace
+
+static int g_dense_variant = -1;   // 1: light variant where it applies (default), 0: heavy variant everywhere
+static int dense_variant() {
+    if (g_dense_variant < 0) {
+        const char* e = getenv("SSF_DENSE_LIGHT");   // measurement switch for bench runs
+        g_dense_variant = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_dense_variant;
+}
+extern "C" int ssf_dense_set_variant(int light) {
+    const int prev = dense_variant();
+    g_dense_variant = light ? 1 : 0;
+    return prev;
+}
 
 extern "C" int ssf_dense_args_bytes(void) { return (int)sizeof(ssf_dense_args); }
 
@@ -462,18 +493,23 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     cfg.resident = (size_t)cfg.nk * wchunk <= (size_t)W_SMEM_MAX;
     cfg.nstage = cfg.resident ? cfg.nk : (int)(W_SMEM_MAX / wchunk);
     if (cfg.nstage > 16) cfg.nstage = 16;
-    cfg.nd = (2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1;
     cfg.n_tiles = (int)((a.rows + 127) / 128);
-    const size_t smem = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8 + (size_t)8 * 32 * STG_LD * 4;
+    const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
+    const size_t smem_light = smem_fixed + (size_t)4 * 32 * STG_LD * 4, smem_heavy = smem_fixed + (size_t)8 * 32 * STG_LD * 4;
+    const int light_mode = dense_variant();
+    const bool light = light_mode && cfg.Nt <= 64 && cfg.resident && smem_light <= (size_t)LIGHT_SMEM_MAX;
+    cfg.nd = light ? 2 : ((2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIGHT_SMEM_MAX);
         if (e != cudaSuccess) return ssf_set_error(e);
         attr_set = true;
     }
-    int n_sm = 148;
-    dim3 grid((unsigned)(cfg.n_tiles < n_sm ? cfg.n_tiles : n_sm), (unsigned)((a.N + 255) / 256));
-    dense_tc_kernel<<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
+    const int n_cta = light ? 2 * 148 : 148;
+    dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));
+    if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem_light, (cudaStream_t)stream>>>(a, cfg);
+    else dense_tc_kernel<2><<<grid, DT_THREADS, smem_heavy, (cudaStream_t)stream>>>(a, cfg);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

@@ -42,6 +42,12 @@ def linear(x1, Wt, cout, w_off1=0, x2=None, w_off2=0, bias=None, act=ACT_NONE, c
 EPI_STORE, EPI_MAX, EPI_DOT = 0, 1, 2
 
 
+def set_dense_variant(light):
+    """Selects the kernel variant of ``dense_tc`` for small layers (include/ssf_dense.h ``ssf_dense_set_variant``); returns the
+    previous setting.  Both variants give bit-identical results."""
+    return bool(nat.lib().ssf_dense_set_variant(1 if light else 0))
+
+
 def dense_tc(wimg, N, K, *, x1=None, x2=None, G=None, offG=0, H=None, offH=0, b1=None, Wd1=None, act1=ACT_NONE, idx=None,
              pos_src=None, pos_q=None, bias=None, Hq=None, Wd2=None, act=ACT_NONE, epi=EPI_STORE, wvec=None, b0=0.0, S=0):
     """Tensor-core dense layer (csrc/dense_tc.cu, include/ssf_dense.h).  Rows: plain ``x1 | x2`` ([..., c]) or the grouped

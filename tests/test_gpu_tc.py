@@ -145,3 +145,39 @@ def test_dense_tc_grouped(B, Nsrc, Nq, S, K, N, epi):
     err = float((y.cpu().double() - ref).abs().max())
     print("dense_tc grouped epi", epi, "max-abs err %.3g" % err, "scale %.3g" % float(ref.abs().max()))
     assert y.shape == ref.shape and err < 3e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("rows,K,N,grouped,epi", [(148 * 128 * 7 + 33, 64, 64, False, 0), (148 * 128 * 5, 96, 64, False, 0),
+                                                  (148 * 128 * 3 + 1, 128, 32, False, 0), (148 * 128 * 9 + 16, 64, 64, True, 1),
+                                                  (148 * 128 * 4 + 64, 32, 64, True, 1), (128 * 40, 192, 64, False, 0),
+                                                  (148 * 128 * 6 + 48, 128, 64, True, 2), (100, 32, 32, False, 0)])
+def test_dense_tc_light_variant_is_bit_identical(rows, K, N, grouped, epi):
+    """N <= 64 layers run the two-CTAs-per-SM variant by default; it must reproduce the one-CTA variant bit for bit."""
+    from ssf_slam_b200 import functional as F_, tc
+    g = torch.Generator().manual_seed(rows + K + N)
+    r = lambda *s: torch.randn(*s, generator=g)
+    W, bias = r(N, K) / K ** 0.5, r(N)
+    img = tc.dense_image(W).cuda()
+    if grouped:
+        S, Nsrc = 16, 777
+        Nq = rows // S
+        G, H, b1, Wd1 = r(1, Nsrc, K).cuda(), r(1, Nq, K).cuda(), r(K).cuda(), (r(3, K) * 0.3).cuda()
+        ps, pq = r(1, Nsrc, 3).cuda(), r(1, Nq, 3).cuda()
+        idx = torch.randint(0, Nsrc, (1, Nq, S), generator=g, dtype=torch.int32).cuda()
+        wv = r(N).cuda()
+        run = lambda: F_.dense_tc(img, N, K, G=G, H=H, b1=b1, Wd1=Wd1, act1=2, idx=idx, pos_src=ps, pos_q=pq, bias=bias.cuda(),
+                                  act=1, epi=epi, wvec=wv, b0=0.5)
+    else:
+        X = r(rows, K).cuda()
+        run = lambda: F_.dense_tc(img, N, K, x1=X, bias=bias.cuda(), act=2)
+    prev = F_.set_dense_variant(True)
+    try:
+        y_light = run()
+        F_.set_dense_variant(False)
+        y_heavy = run()
+    finally:
+        F_.set_dense_variant(prev)
+    assert torch.equal(y_light, y_heavy)
+    if not grouped:
+        ref = _act(X.cpu().double() @ W.double().t() + bias.double(), 2)
+        assert float((y_light.cpu().double() - ref).abs().max()) < 3e-6 * max(1.0, float(ref.abs().max()))

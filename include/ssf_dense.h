@@ -40,10 +40,10 @@ typedef struct ssf_dense_args {
 extern "C" {
 #endif
 int ssf_dense_tc(const ssf_dense_args* args, void* stream);
-/* Layers with N <= 64 and a small weight image run a light kernel variant (288 threads, 256 TMEM columns, two CTAs per SM)
- * by default; ssf_dense_set_variant(0) forces the one-CTA-per-SM variant everywhere (results are bit-identical).  Returns
- * the previous setting. */
-int ssf_dense_set_variant(int light);
+/* Layers with N <= 64 and a small weight image can run a light kernel variant (288 threads, 256 TMEM columns, two CTAs per
+ * SM).  mode 0: never; 1 (default): where it measured faster (pooled plain-row layers); 2: every eligible layer.  Results are
+ * bit-identical across modes.  Returns the previous mode. */
+int ssf_dense_set_variant(int mode);
 int ssf_dense_args_bytes(void);   /* sizeof(ssf_dense_args) as compiled, for binding self-checks */
 #ifdef __cplusplus
 }

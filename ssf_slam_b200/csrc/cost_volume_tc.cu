@@ -48,6 +48,11 @@ struct CvTcArgs {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ssf_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // integer round-to-nearest (ties away) to the TF32 grid == cvt.rna.tf32.f32 for finite values; lo is exact
@@ -226,6 +231,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
             return (size_t)b_ * a.N1 + (n_ < a.N1 ? n_ : a.N1 - 1);
         };
         int id_next = n_my > 0 ? __ldg(idx_br + tile_qrow(0) * 16 + s) : 0;
+        // Gathered rows Gab[idx] of tile `it_` (this warp's 32 rows x 32 columns) -> the warp's own staging sub-tile, by
+        // cp.async: issued as soon as the sub-tile is free in the previous tile, so the gather latency hides behind E2..E6
+        auto gather_issue = [&](int it_, int id_) {
+            const int tile_ = (int)blockIdx.x + it_ * (int)gridDim.x;
+            const int b_ = tile_ / a.tiles_per_cloud;
+            const float* gbase = a.Gab + (size_t)b_ * a.N2 * (2 * CM) + br * CM + c0 + pc * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rl = j * 4 + rg;
+                const int sid = __shfl_sync(0xffffffffu, id_, rl);
+                cp_async16(stage_w + rl * LDA + pc * 4, gbase + (size_t)sid * (2 * CM));
+            }
+            cp_async_commit();
+        };
+        if (n_my > 0) gather_issue(0, id_next);
         // Hab rows of the 8 points of a tile: 256 float4, one per thread of warps 0-7; tile `it` sits in buffer it & 1
         auto hab_load = [&](int it_) -> float4 {
             const int tile_ = (int)blockIdx.x + it_ * (int)gridDim.x;
@@ -262,14 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
             float v[32];
             // ---- prologue: x0 = leaky(Gab[idx] + Hab[n])  (first layers of mlp_convs / mlp_convs2, split algebraically)
             {
-                const float* gbase = a.Gab + (size_t)b * a.N2 * (2 * CM) + br * CM + c0 + pc * 4;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int rl = j * 4 + rg;
-                    const int sid = __shfl_sync(0xffffffffu, id, rl);
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gbase + (size_t)sid * (2 * CM)));
-                    *reinterpret_cast<float4*>(stage_w + rl * LDA + pc * 4) = g4;
-                }
+                cp_async_wait_all();   // rows gathered by gather_issue(it)
                 __syncwarp();
                 const float* hab = sHab + (it & 1) * (8 * 2 * CM) + p * (2 * CM) + br * CM + c0;
                 const float* mine = sOwn + r * LDA + c0;
@@ -452,6 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
             }
             named_bar(1, 512);   // mixed rows consumed (sOwn is reused as a staging tile below and by the next tile)
             TRACE(br, 5);
+            if (br == 0 && it + 1 < n_my) gather_issue(it + 1, id_next);   // the forward branch does not touch sA again in this tile
             // v[] now holds this thread's 32 columns of the mixed row (A' or Aw'); it stays in registers through E2,
             // which therefore works on 16 columns at a time
             // ---- E2: C1 = leaky(D + H3[n] + W3d . dir)   (first layer of mlp_convs3; A block came from the MMA)
@@ -521,6 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
                     }
                 }
                 __syncwarp();
+                if (it + 1 < n_my) gather_issue(it + 1, id_next);   // staging sub-tile free again
             }
             TRACE(br, 9);
             // ---- E4: T1 = relu(D + bn1)

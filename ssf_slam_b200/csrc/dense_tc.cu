@@ -453,17 +453,17 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
 
 }  // namespace
 
-static int g_dense_variant = -1;   // 1: light variant where it applies (default), 0: heavy variant everywhere
+static int g_dense_variant = -1;   // 0: heavy variant everywhere, 1: light variant where it pays (default), 2: wherever eligible
 static int dense_variant() {
     if (g_dense_variant < 0) {
         const char* e = getenv("SSF_DENSE_LIGHT");   // measurement switch for bench runs
-        g_dense_variant = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_dense_variant = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     }
     return g_dense_variant;
 }
 extern "C" int ssf_dense_set_variant(int light) {
     const int prev = dense_variant();
-    g_dense_variant = light ? 1 : 0;
+    g_dense_variant = light < 0 ? 0 : (light > 2 ? 2 : light);
     return prev;
 }
 
@@ -497,7 +497,10 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
     const size_t smem_light = smem_fixed + (size_t)4 * 32 * STG_LD * 4, smem_heavy = smem_fixed + (size_t)8 * 32 * STG_LD * 4;
     const int light_mode = dense_variant();
-    const bool light = light_mode && cfg.Nt <= 64 && cfg.resident && smem_light <= (size_t)LIGHT_SMEM_MAX;
+    // light_mode 1: only where it measured faster (pooled plain-row layers: the epilogue warps are the bottleneck and the
+    // producers are cheap); 2: every eligible layer (tests)
+    const bool light = light_mode && cfg.Nt <= 64 && cfg.resident && smem_light <= (size_t)LIGHT_SMEM_MAX &&
+                       (light_mode == 2 || (a.epi_mode == SSF_EPI_MAX && a.a_mode == 0));
     cfg.nd = light ? 2 : ((2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1);
     static bool attr_set = false;
     if (!attr_set) {

@@ -42,10 +42,10 @@ def linear(x1, Wt, cout, w_off1=0, x2=None, w_off2=0, bias=None, act=ACT_NONE, c
 EPI_STORE, EPI_MAX, EPI_DOT = 0, 1, 2
 
 
-def set_dense_variant(light):
-    """Selects the kernel variant of ``dense_tc`` for small layers (include/ssf_dense.h ``ssf_dense_set_variant``); returns the
-    previous setting.  Both variants give bit-identical results."""
-    return bool(nat.lib().ssf_dense_set_variant(1 if light else 0))
+def set_dense_variant(mode):
+    """Kernel-variant policy of ``dense_tc`` for small layers (include/ssf_dense.h ``ssf_dense_set_variant``: 0 one CTA per SM
+    everywhere, 1 default policy, 2 light variant wherever eligible); returns the previous mode.  Results are bit-identical."""
+    return int(nat.lib().ssf_dense_set_variant(int(mode)))
 
 
 def dense_tc(wimg, N, K, *, x1=None, x2=None, G=None, offG=0, H=None, offH=0, b1=None, Wd1=None, act1=ACT_NONE, idx=None,

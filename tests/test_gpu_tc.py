@@ -170,14 +170,21 @@ def test_dense_tc_light_variant_is_bit_identical(rows, K, N, grouped, epi):
     else:
         X = r(rows, K).cuda()
         run = lambda: F_.dense_tc(img, N, K, x1=X, bias=bias.cuda(), act=2)
-    prev = F_.set_dense_variant(True)
+    prev = F_.set_dense_variant(2)
     try:
         y_light = run()
-        F_.set_dense_variant(False)
+        F_.set_dense_variant(0)
         y_heavy = run()
     finally:
         F_.set_dense_variant(prev)
     assert torch.equal(y_light, y_heavy)
     if not grouped:
         ref = _act(X.cpu().double() @ W.double().t() + bias.double(), 2)
-        assert float((y_light.cpu().double() - ref).abs().max()) < 3e-6 * max(1.0, float(ref.abs().max()))
+    else:   # MAX / DOT without a per-row epilogue term: bias and activation are applied after the pooling
+        li = idx.cpu().long()[0]
+        dirs = (ps.cpu()[0][li] - pq.cpu()[0][:, None, :]).double()
+        A = _act(G.cpu()[0][li].double() + H.cpu()[0][:, None, :].double() + b1.cpu().double() + dirs @ Wd1.cpu().double(), 2)
+        D = _act(A @ W.double().t() + bias.double(), 1)
+        ref = (D.max(dim=1).values if epi == 1 else D @ wv.cpu().double() + 0.5)[None]
+    assert y_light.shape == ref.shape
+    assert float((y_light.cpu().double() - ref).abs().max()) < 3e-6 * max(1.0, float(ref.abs().max()))

@@ -152,6 +152,16 @@ int ssf_frontend(const float* points, const float* flow, int B, int N, int mode,
                  const int* sem, unsigned long long movable_bits, const int* inst, int n_inst, float tau,
                  unsigned char* mask_out, double* odom_out, double* pose_out, void* stream);
 
+/* ---- the reference's noSeg masker on the device: 2-component full-covariance Gaussian mixture by EM on [flow | xyz],
+ * majority component = background.  Replaces `GaussianMixture(n_components=2).fit_predict(...)` + `Counter.most_common(1)` at
+ * scripts/PointCloudOdometry_noSeg.py:97-103 and ASF/main_sju_occ_ros.py:257-263 (scikit-learn defaults: tol 1e-3, reg_covar
+ * 1e-6, max_iter 100, one initialisation); the k-means seeding the reference draws from the global RNG is deterministic here
+ * (specification pinned against scikit-learn: oracle/gmm.py).  points, flow [B,N,3] f32 -> mask u8 [B,N] (0 = background),
+ * info f64 [B,4] = (EM iterations, lower bound, converged, background count) or NULL.  Feed the mask to ssf_frontend mode 0
+ * for the pose. */
+int ssf_gmm_mask(const float* points, const float* flow, int B, int N, int max_iter, double tol, unsigned char* mask_out,
+                 double* info_out, void* stream);
+
 /* ---- tensor-core bring-up / regression: Y[128,N] = X[128,K].W[N,K]^T on tcgen05 kind::tf32 (3xTF32 when passes == 3);
  * Whi_img / Wlo_img are the split weights in the no-swizzle K-major UMMA image (ssf_slam_b200.tc.weight_image);
  * mode 0: A operand from TMEM, mode 1: A operand from shared memory */

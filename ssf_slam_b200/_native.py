@@ -12,8 +12,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssf_b200.so")
 
-_P, _I, _F, _U64, _I64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_longlong
-_CODES = {"p": _P, "i": _I, "f": _F, "Q": _U64, "q": _I64}
+_P, _I, _F, _U64, _I64, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_longlong, ctypes.c_double
+_CODES = {"p": _P, "i": _I, "f": _F, "Q": _U64, "q": _I64, "d": _D}
 
 # name -> (argument codes, restype); mirrors include/ssf_b200.h one to one
 SIGNATURES = {
@@ -53,6 +53,7 @@ SIGNATURES = {
     "ssf_dense_args_bytes": ("", _I),
     "ssf_dense_set_variant": ("i", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
+    "ssf_gmm_mask": ("ppiiidppp", _I),
     "ssf_plane_features_workspace_bytes": ("ii", _I64),
     "ssf_plane_features": ("piiiiifipppp", _I),
     "ssf_tc_gemm_test": ("pppiiiipp", _I),

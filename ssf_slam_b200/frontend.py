@@ -9,6 +9,10 @@ Mirrors, with NumPy arrays in and out exactly like the reference's in-process co
 * ``background_index(points, flow, ...) -> bg_index`` -- stands where the drivers compute ``bg_index`` from the GMM
   (ASF/main_sju_occ_ros.py:257-263) or the GT mask (scripts/PointCloudOdometry.py:91): the deterministic
   residual-vs-rigid-flow masker with optional per-instance voting.
+* ``gmm_background(points, flow) -> bg_index`` -- the reference's own noSeg masker, the three lines
+  ``GaussianMixture(n_components=2).fit_predict(hstack(flow, points))`` / ``Counter.most_common`` / ``argwhere``
+  (scripts/PointCloudOdometry_noSeg.py:97-103, ASF/main_sju_occ_ros.py:257-263), fitted on the GPU by EM with scikit-learn's
+  defaults and a deterministic seeding (csrc/gmm.cu; specification pinned against scikit-learn in oracle/gmm.py).
 * ``odometry(points, flow, ...)`` -- mask + pose + the ``frame_odom1`` payload ``[tx,ty,tz,qx,qy,qz,qw]`` in one launch.
 * ``SceneFlowFrontEnd`` -- network + mask + ego-motion for batches of frame pairs held in HOST memory (the end-to-end
   call ``bench.py`` times: H2D of the clouds, all kernels, D2H of masks and poses).
@@ -34,10 +38,11 @@ def slove_RT_by_SVD(src, dst, device="cuda:0"):
     return pose[:9].reshape(3, 3).copy(), pose[9:].reshape(3, 1).copy()
 
 
-def odometry(points, flow, mask=None, sem=None, inst=None, movable=(), tau=0.10, device="cuda:0"):
+def odometry(points, flow, mask=None, sem=None, inst=None, movable=(), tau=0.10, device="cuda:0", masker="residual"):
     """points, flow [N,3] (or [B,N,3]) -> dict(mask u8, bg_index, odom f64[7] = [t, qx,qy,qz,qw], R, t).
     ``mask`` given (0 = background, as ``s_fg_mask``) -> pose from those points only (GT-mask variants);
-    otherwise the residual masker runs (noSeg), seeded/voted by ``sem``/``inst`` when given (Seg)."""
+    otherwise the residual masker runs (noSeg), seeded/voted by ``sem``/``inst`` when given (Seg), or -- ``masker="gmm"`` --
+    the reference's 2-component Gaussian-mixture masker."""
     nat.require_device()
     p = np.asarray(points, np.float32)
     single = p.ndim == 2
@@ -47,6 +52,9 @@ def odometry(points, flow, mask=None, sem=None, inst=None, movable=(), tau=0.10,
     tp, tf = _dev(p, torch.float32, device), _dev(f, torch.float32, device)
     if mask is not None:
         tm = _dev(np.asarray(mask).reshape(p.shape[:2]) != 0, torch.uint8, device)
+        m, odom, pose = F_.frontend(tp, tf, mode=0, in_mask=tm, want_pose=True)
+    elif masker == "gmm":
+        tm = F_.gmm_mask(tp, tf)
         m, odom, pose = F_.frontend(tp, tf, mode=0, in_mask=tm, want_pose=True)
     else:
         ts = None if sem is None else _dev(np.asarray(sem).reshape(p.shape[:2]), torch.int32, device)
@@ -64,6 +72,12 @@ def odometry(points, flow, mask=None, sem=None, inst=None, movable=(), tau=0.10,
 def background_index(points, flow, sem=None, inst=None, movable=(), tau=0.10, device="cuda:0"):
     """bg_index (ascending int64) of the static points, the quantity the drivers feed to slove_RT_by_SVD."""
     return odometry(points, flow, sem=sem, inst=inst, movable=movable, tau=tau, device=device)["bg_index"]
+
+
+def gmm_background(points, flow, device="cuda:0"):
+    """bg_index of the majority component of a 2-component GMM on [flow | xyz]: what the reference's noSeg drivers compute
+    with scikit-learn on the host (scripts/PointCloudOdometry_noSeg.py:97-103)."""
+    return odometry(points, flow, device=device, masker="gmm")["bg_index"]
 
 
 class _Pending:
@@ -85,9 +99,11 @@ class SceneFlowFrontEnd:
     overlap on the GPU (one batch's H2D / D2H copies and its latency-bound kernels such as FPS run under the other's dense
     kernels).  Frame pairs are independent (ASF/main_sju_occ_ros.py:168-284), so this is plain pipelining."""
 
-    def __init__(self, net, device="cuda:0", tau=0.10, movable=(), n_slots=2, use_graph=False):
+    def __init__(self, net, device="cuda:0", tau=0.10, movable=(), n_slots=2, use_graph=False, masker="residual"):
         nat.require_device()
-        self.net, self.device, self.tau, self.movable = net, torch.device(device), tau, tuple(movable)
+        if masker not in ("residual", "gmm"):
+            raise ValueError("masker must be 'residual' (DESIGN.md section 5) or 'gmm' (the reference's noSeg masker)")
+        self.net, self.device, self.tau, self.movable, self.masker = net, torch.device(device), tau, tuple(movable), masker
         self._pin = {}
         self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n_slots)]
         self._pending = [None] * n_slots
@@ -119,7 +135,10 @@ class SceneFlowFrontEnd:
     def _run(self, x1, x2, ts, ti, n_inst):
         flows, _ = self.net.forward_pm(x1, x2)
         flow = flows[0] if flows[0].shape[-1] == 3 else flows[0][..., :3].contiguous()   # 4-channel heads: xyz flow only
-        mask, odom = F_.frontend(x1, flow, mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
+        if self.masker == "gmm":
+            mask, odom = F_.frontend(x1, flow, mode=0, in_mask=F_.gmm_mask(x1, flow))
+        else:
+            mask, odom = F_.frontend(x1, flow, mode=1, sem=ts, movable=self.movable, inst=ti, n_inst=n_inst, tau=self.tau)
         return flows[0], mask, odom
 
     def _graph_for(self, slot, B, N, seg, n_inst):

@@ -258,3 +258,14 @@ def frontend(points, flow, mode=1, in_mask=None, sem=None, movable=(), inst=None
                                      nat.ptr(inst), int(n_inst), float(tau), nat.ptr(mask), nat.ptr(odom), nat.ptr(pose),
                                      nat.stream()))
     return (mask, odom, pose) if want_pose else (mask, odom)
+
+
+def gmm_mask(points, flow, max_iter=100, tol=1e-3, want_info=False):
+    """The reference's noSeg masker (2-component GMM on [flow | xyz], majority = background; csrc/gmm.cu).
+    points, flow f32 [B,N,3] -> mask u8 [B,N] (0 = background) (, info f64 [B,4] = n_iter, lower bound, converged, bg count)."""
+    B, N, _ = points.shape
+    mask = torch.empty(B, N, dtype=torch.uint8, device=points.device)
+    info = torch.empty(B, 4, dtype=torch.float64, device=points.device) if want_info else None
+    nat.check(nat.lib().ssf_gmm_mask(nat.ptr(points), nat.ptr(flow), B, N, int(max_iter), float(tol), nat.ptr(mask), nat.ptr(info),
+                                     nat.stream()))
+    return (mask, info) if want_info else mask

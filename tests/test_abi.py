@@ -24,7 +24,7 @@ def _kind(arg):
     if "*" in arg:
         return "p"
     t = arg.rsplit(" ", 1)[0].strip()
-    return {"int": "i", "float": "f", "unsigned long long": "Q", "long long": "q"}[t]
+    return {"int": "i", "float": "f", "double": "d", "unsigned long long": "Q", "long long": "q"}[t]
 
 
 @pytest.fixture(scope="module")

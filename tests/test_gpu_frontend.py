@@ -73,3 +73,75 @@ def test_batched_frontend_equals_single():
     for b in range(4):
         want = ofe.masker_spec(p[b], f[b], 0.1)
         assert np.array_equal(m[b].cpu().numpy(), want["mask"]) and np.array_equal(o[b].cpu().numpy(), want["odom"])
+
+
+# ------------------------------------------------------------------ the reference's own noSeg masker (GMM) on the GPU
+
+def _gmm_gpu(p, f):
+    from ssf_slam_b200 import functional as F_
+    tp, tf = torch.from_numpy(np.ascontiguousarray(p)).cuda(), torch.from_numpy(np.ascontiguousarray(f)).cuda()
+    if tp.dim() == 2:
+        tp, tf = tp[None], tf[None]
+    m, info = F_.gmm_mask(tp, tf, want_info=True)
+    return m.cpu().numpy(), info.cpu().numpy()
+
+
+def test_gmm_mask_matches_sklearn_golden(golden_dir):
+    """Labels written by scikit-learn's GaussianMixture itself (oracle/gen_golden_gmm.py) from the spec's initial parameters."""
+    from oracle import gmm as ogmm
+    g = np.load(os.path.join(golden_dir, "gmm_mask.npz"))
+    for name in ("gt0", "gt3", "gt7", "tiny"):
+        m, info = _gmm_gpu(g[name + "_points"], g[name + "_flow"])
+        assert np.array_equal(m[0], g[name + "_mask"]), name
+        assert int(info[0, 0]) == int(g[name + "_n_iter"]) and info[0, 2] == 1.0, name
+        assert abs(info[0, 1] - float(g[name + "_sklearn_lower_bound"])) < 1e-8, name
+        bg = np.flatnonzero(m[0] == 0)
+        assert np.array_equal(bg, ogmm.reference_bg_index(g[name + "_sklearn_labels"].astype(np.int64))), name
+        assert int(info[0, 3]) == len(bg)
+
+
+@pytest.mark.parametrize("n,seed", [(8192, 21), (16384, 22), (1000, 23), (300, 24)])
+def test_gmm_mask_random_vs_spec(n, seed):
+    from oracle import gmm as ogmm
+    from ssf_slam_b200 import frontend, synth
+    it = synth.make_sequence(seed, 1, n)[0]
+    f = (it["gt"] + np.random.default_rng(seed).normal(0, 0.02, it["gt"].shape)).astype(np.float32)
+    want = ogmm.gmm_spec(it["pos1"], f)
+    m, info = _gmm_gpu(it["pos1"], f)
+    assert np.array_equal(m[0], want["mask"])
+    assert int(info[0, 0]) == want["n_iter"] and abs(info[0, 1] - want["lower_bound"]) < 1e-8
+    # drop-in calls: bg_index, and the pose the reference's slove_RT_by_SVD gives on that bg_index
+    assert np.array_equal(frontend.gmm_background(it["pos1"], f), want["bg_index"])
+    out = frontend.odometry(it["pos1"], f, masker="gmm")
+    R, t = ofe.reference_pose(it["pos1"], f, want["bg_index"])
+    assert np.allclose(out["R"], R, atol=1e-5) and np.allclose(out["t"], t.ravel(), atol=1e-4)
+
+
+def test_gmm_mask_batched_equals_single():
+    from ssf_slam_b200 import synth
+    its = synth.make_sequence(31, 3, 4096)
+    p = np.stack([it["pos1"] for it in its])
+    f = np.stack([(it["gt"] + np.random.default_rng(i).normal(0, 0.02, it["gt"].shape)).astype(np.float32) for i, it in enumerate(its)])
+    mb, ib = _gmm_gpu(p, f)
+    for b in range(3):
+        m1, i1 = _gmm_gpu(p[b], f[b])
+        assert np.array_equal(mb[b], m1[0]) and np.array_equal(ib[b], i1[0])
+
+
+def test_frontend_gmm_masker_end_to_end():
+    """SceneFlowFrontEnd(masker='gmm'): network flow -> GMM mask -> pose, equal to the stages called one by one."""
+    from ssf_slam_b200 import functional as F_, synth
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200.weights import random_init_state_dict
+    net = TFlow()
+    net.load_state_dict(random_init_state_dict(0))
+    net = net.cuda().eval()
+    its = synth.make_sequence(41, 2, 2048)
+    p1, p2 = np.stack([it["pos1"] for it in its]), np.stack([it["pos2"] for it in its])
+    out = SceneFlowFrontEnd(net, masker="gmm").process(p1, p2, return_flow=True)
+    flow = out["flow"].cuda()
+    x1 = torch.from_numpy(p1).cuda()
+    m = F_.gmm_mask(x1, flow)
+    _, odom = F_.frontend(x1, flow, mode=0, in_mask=m)
+    assert torch.equal(out["mask"], m.cpu()) and torch.equal(out["odom"], odom.cpu())

@@ -108,3 +108,18 @@ def test_tflow_port_matches_reference_golden(golden_dir, oracle_c, n, name, ch):
     for i in range(4):
         # bit-exact in the build container; allow for a different CPU's MKL/oneDNN code path elsewhere
         assert flows[i].shape[1] == ch and np.abs(flows[i][0].numpy() - g["flow%d" % i]).max() <= 2e-5
+
+
+def test_gmm_spec_matches_sklearn_golden_and_live(golden_dir):
+    """oracle/gmm.py (restatement of scikit-learn's EM, the reference's noSeg masker) against labels written by scikit-learn
+    itself, and against scikit-learn run now from the same initial parameters."""
+    from oracle import gmm
+    g = np.load(os.path.join(golden_dir, "gmm_mask.npz"))
+    for name in ("gt0", "gt3", "gt7", "tiny"):
+        spec = gmm.gmm_spec(g[name + "_points"], g[name + "_flow"])
+        assert np.array_equal(spec["labels"], g[name + "_sklearn_labels"].astype(np.int64)), name
+        assert np.array_equal(spec["mask"], g[name + "_mask"]) and spec["n_iter"] == int(g[name + "_n_iter"]), name
+        assert abs(spec["lower_bound"] - float(g[name + "_sklearn_lower_bound"])) < 1e-9
+    spec, labels, gm = gmm.check_against_sklearn(g["gt0_points"], g["gt0_flow"])
+    assert np.array_equal(labels, spec["labels"]) and gm.n_iter_ == spec["n_iter"]
+    assert np.array_equal(gmm.reference_bg_index(labels), spec["bg_index"])

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--graph", action="store_true", help="e2e / latency legs: CUDA-graph replay of the step instead of eager "
                     "launches (measured equal on B200: the step is bound by kernel time, not by launch cost)")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams independent batches are pipelined over")
+    ap.add_argument("--masker", default="residual", choices=["residual", "gmm"], help="dynamic-point masker of the step: the "
+                    "residual-vs-rigid-flow masker (north star, DESIGN.md section 5) or the reference's noSeg GMM masker on the GPU")
     ap.add_argument("--shares-out", default=None, help="write the full per-kernel CUDA-event table (JSON) to this path")
     return ap.parse_args()
 
@@ -245,7 +247,7 @@ def main():
     sd = random_init_state_dict(0)
     net = TFlow()
     net.load_state_dict(sd, strict=True)
-    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=max(1, args.streams), use_graph=args.graph)   # also prepares the weight images
+    fe = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=max(1, args.streams), use_graph=args.graph, masker=args.masker)   # also prepares the weight images
     d1, d2 = torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)
     dev_batches = [(d1[batch_ids(s)].contiguous(), d2[batch_ids(s)].contiguous()) for s in range(max(1, min(K + Wm, POOL)))]
 
@@ -254,15 +256,20 @@ def main():
     NS = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
 
+    def mask_pose(x1, flow):
+        if args.masker == "gmm":
+            return F_.frontend(x1, flow, mode=0, in_mask=F_.gmm_mask(x1, flow))
+        return F_.frontend(x1, flow, mode=1, tau=0.10)
+
     def device_step(s, keep, stream=None):
         x1, x2 = dev_batches[s % len(dev_batches)]
         if stream is None:
             flows, _ = net.forward_pm(x1, x2)
-            mask, odom = F_.frontend(x1, flows[0], mode=1, tau=0.10)
+            mask, odom = mask_pose(x1, flows[0])
         else:
             with torch.cuda.stream(stream):
                 flows, _ = net.forward_pm(x1, x2)
-                mask, odom = F_.frontend(x1, flows[0], mode=1, tau=0.10)
+                mask, odom = mask_pose(x1, flows[0])
         keep.append((mask, odom))
 
     def sync_all():
@@ -333,7 +340,7 @@ def main():
     ems = float(ems.item())
 
     # ---- single-pair latency (the reference's operating point: one frame pair per 100 ms tick), host buffers in and out,
-    fe1 = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=1, use_graph=args.graph)
+    fe1 = SceneFlowFrontEnd(net, device=dev, tau=0.10, n_slots=1, use_graph=args.graph, masker=args.masker)
     one = (torch.from_numpy(p1[:1]), torch.from_numpy(p2[:1]))
     for _ in range(5):
         fe1.process(*one)
@@ -356,6 +363,28 @@ def main():
     keep.clear()
 
     point_ops = point_op_rooflines(B, N, dev) if rank == 0 else None
+
+    # ---- the two maskers stand-alone on the step's batch (ground-truth flow + 2 cm noise, so that there are movers to find)
+    maskers = None
+    if rank == 0:
+        gt = np.stack([pool[i]["gt"] for i in batch_ids(0)])
+        gflow = torch.from_numpy((gt + np.random.default_rng(0).normal(0, 0.02, gt.shape)).astype(np.float32)).to(dev)
+        x1 = dev_batches[0][0]
+        maskers = {}
+        for name, fn in (("residual", lambda: F_.frontend(x1, gflow, mode=1, tau=0.10)),
+                         ("gmm", lambda: F_.frontend(x1, gflow, mode=0, in_mask=F_.gmm_mask(x1, gflow)))):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(5):
+                fn()
+            m1.record()
+            torch.cuda.synchronize()
+            maskers[name] = {"ms_per_batch": m0.elapsed_time(m1) / 5, "clouds": B, "bytes_per_cloud": N * 25 + 56}
+        _, info = F_.gmm_mask(x1, gflow, want_info=True)
+        maskers["gmm"]["em_iterations_mean"] = float(info[:, 0].mean().item())
 
     if rank != 0:
         if world > 1:
@@ -396,7 +425,7 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic CARLA-shaped clouds (ssf_slam_b200/synth.py), random-init TFlow weights (seed 0)",
             "config": {"workload": "configs[1]: 200-frame synthetic sequence shaped like rm_road/SF/00, N=%d, "
-                                   "noSeg_ActiveSceneFlow pipeline (flow + dynamic mask + ego-motion)" % N,
+                                   "noSeg_ActiveSceneFlow pipeline (flow + dynamic mask + ego-motion)" % N, "masker": args.masker,
                        "pairs_per_step_per_gpu": B, "distinct_pairs": POOL, "sharding": "sequence id %% world (config 4), no "
                        "collective on the hot path; one final all_gather of poses+masks",
                        "pipelining": "independent batches alternate over %d CUDA streams (per-stream pinned staging in the e2e leg)" % NS,
@@ -406,7 +435,7 @@ def main():
                     "ms_per_step": ems / K},
             "latency": {"pairs": 1, "ms_per_pair": latency_ms, "note": "SceneFlowFrontEnd.process on one host-resident frame pair "
                         "(H2D + %s + D2H), mean of 20" % ("CUDA-graph replay" if args.graph else "eager launches")},
-            "roofline": roof, "point_ops": point_ops, "kernel_shares": {k: round(v["share"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+            "roofline": roof, "point_ops": point_ops, "maskers": maskers, "kernel_shares": {k: round(v["share"], 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
 
     if not args.no_cpu_baseline and world == 1:
         import torch as _t

@@ -5,7 +5,7 @@ import torch
 from . import functional as F_
 
 _NAMES = ("linear", "dense_tc", "attention_mix", "softmax_pool", "gather_rows", "transpose", "fps", "knn_idx", "interpolate", "group_mlp_max", "cost_volume",
-          "build_csr", "segment_softmax_sum", "frontend")
+          "build_csr", "segment_softmax_sum", "frontend", "gmm_mask")
 _orig = {}
 _records = []
 

@@ -419,6 +419,15 @@ def main():
             roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
                     "traffic": None, "peak_source": pk["source"]}
 
+    if roof is not None:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same batch only)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+            if tr is not None and tr["batch"] == B:
+                roof["traffic"] = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+                roof["traffic_source"] = tr["capture"]
+        except (OSError, ValueError, KeyError):
+            pass
+
     value = world * B * K / (ms * 1e-3)
     e2e = world * B * K / (ems * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,

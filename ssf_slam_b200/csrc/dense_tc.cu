@@ -30,7 +30,7 @@ constexpr int KC = 32;                    // K chunk
 constexpr int AS = 4;                     // TMEM A stages (64 columns each: hi | lo)
 constexpr int DT_THREADS = 448;           // heavy variant: 2 producer warpgroups, 1 CTA per SM
 constexpr int DT_THREADS_LIGHT = 288;     // light variant: 1 producer warpgroup, 2 CTAs per SM (small layers)
-constexpr int W_SMEM_MAX = 160 * 1024;    // bytes of shared memory for weight images
+constexpr int W_SMEM_MAX = 150 * 1024;    // bytes of shared memory for weight images
 constexpr int LIGHT_SMEM_MAX = 112 * 1024; // per-CTA shared memory of the light variant (two CTAs per SM)
 constexpr int STG_LD = KC + 4;            // row stride (floats) of a producer warp's transpose tile
 
@@ -41,6 +41,7 @@ struct DenseCfg {
     int resident;    // whole image resident (nk <= nstage)
     int nd;          // accumulator buffers
     int n_tiles;     // row tiles
+    int wsplit;      // bulk copies per streamed weight chunk
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -77,16 +78,23 @@ struct RowCtx {
     float qx, qy, qz; // pos_q[pt]
 };
 
-// NPROD = 2: the heavy variant (448 threads, all 512 TMEM columns, one CTA per SM).  NPROD = 1: the light variant for
-// layers whose weight image is small (320 threads, 256 TMEM columns, <= 110 KB shared memory -> two CTAs per SM, i.e. two
-// independent tile pipelines and 20 warps per SM instead of 14; these kernels are bound by warps in flight).
-template <int NPROD>
-__global__ void __launch_bounds__(NPROD == 2 ? DT_THREADS : DT_THREADS_LIGHT, NPROD == 2 ? 1 : 2)
+// VARIANT 0 (heavy): two producer warpgroups, one epilogue warpgroup, 448 threads, all 512 TMEM columns, one CTA per SM.
+// VARIANT 1 (light): for layers whose weight image is small: one producer warpgroup, 288 threads, 256 TMEM columns, <= 112 KB
+//                    shared memory -> two CTAs per SM, i.e. two independent tile pipelines (the MMA warp also fetches the
+//                    resident weights).
+// VARIANT 2 (wide):  for 256-column tiles, whose accumulator cannot be double buffered (the epilogue and the next tile's MMAs
+//                    serialise): one producer warpgroup with all four A stages and TWO epilogue warpgroups, each draining
+//                    half of the columns.
+template <int VARIANT>
+__global__ void __launch_bounds__(VARIANT == 1 ? DT_THREADS_LIGHT : DT_THREADS, VARIANT == 1 ? 2 : 1)
 dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
-    constexpr int NTHR = NPROD == 2 ? DT_THREADS : DT_THREADS_LIGHT;
-    constexpr int W_EPI = 4 * NPROD;          // first epilogue warp
-    constexpr int W_MMA = W_EPI + 4, W_TMA = NPROD == 2 ? W_EPI + 5 : W_EPI + 4;   // light: resident weights, the MMA warp fetches them
-    constexpr uint32_t TCOLS = NPROD == 2 ? 512 : 256;
+    constexpr int NPROD = VARIANT == 0 ? 2 : 1;   // producer warpgroups
+    constexpr int NEPI = VARIANT == 2 ? 2 : 1;    // epilogue warpgroups
+    constexpr int SPW = VARIANT == 2 ? 4 : 2;     // A stages per producer warpgroup
+    constexpr int NTHR = VARIANT == 1 ? DT_THREADS_LIGHT : DT_THREADS;
+    constexpr int W_EPI = 4 * NPROD;              // first epilogue warp
+    constexpr int W_MMA = W_EPI + 4 * NEPI, W_TMA = VARIANT == 1 ? W_MMA : W_MMA + 1;
+    constexpr uint32_t TCOLS = VARIANT == 1 ? 256 : 512;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Nt = cfg.Nt, nk = cfg.nk;
     const int n0 = blockIdx.y * 256;                       // first output column of this CTA
@@ -106,7 +114,8 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
     uint64_t* d_full = bars + 40;                   // [2]
     uint64_t* d_empty = bars + 42;                  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
-    float* sStage = reinterpret_cast<float*>(bars + 46);   // [8 producer warps][32 rows][STG_LD]
+    float* sStage = reinterpret_cast<float*>(bars + 46);   // [4 NPROD producer warps][32 rows][STG_LD]
+    float* sEpi = sStage + 4 * NPROD * (32 * STG_LD);      // [4 NEPI epilogue warps][32 rows][STG_LD]  (STORE epilogue)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == W_MMA) tc_alloc(tmem_slot, TCOLS);
@@ -121,7 +130,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
         }
         for (int i = 0; i < 2; ++i) {
             ssf_mbar_init(&d_full[i], 1);
-            ssf_mbar_init(&d_empty[i], 128);
+            ssf_mbar_init(&d_empty[i], 128 * NEPI);
         }
         ssf_mbar_fence_init();
     }
@@ -155,15 +164,17 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 const int st = g % cfg.nstage;
                 if (g >= cfg.nstage) ssf_mbar_wait(&w_empty[st], (uint32_t)((g / cfg.nstage - 1) & 1));
                 ssf_mbar_expect_tx(&w_full[st], wchunk);
-                ssf_bulk_g2s(sW + (size_t)st * wchunk, wsrc + (size_t)(g % nk) * wchunk, wchunk, &w_full[st]);
+                const uint32_t part = wchunk / (uint32_t)cfg.wsplit;
+                for (int pp = 0; pp < cfg.wsplit; ++pp)
+                    ssf_bulk_g2s(sW + (size_t)st * wchunk + pp * part, wsrc + (size_t)(g % nk) * wchunk + pp * part, part, &w_full[st]);
             }
         }
     };
-    if (NPROD == 2 && warp == W_TMA) {
+    if (VARIANT != 1 && warp == W_TMA) {
         if (lane == 0) produce_weights();
         __syncwarp();
     } else if (warp == W_MMA) {
-        if (NPROD == 1) {
+        if (VARIANT == 1) {
             if (lane == 0) produce_weights();
             __syncwarp();
         }
@@ -182,13 +193,13 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 for (int kc = 0; kc < nk; ++kc) {
                     const int g = it * nk + kc;
                     const int j = (it / NPROD) * nk + kc;             // chunk count of the producing warpgroup
-                    const int ws = cfg.resident ? kc : g % cfg.nstage, as = (it % NPROD) * 2 + (j & 1);
+                    const int ws = cfg.resident ? kc : g % cfg.nstage, as = (it % NPROD) * SPW + (j % SPW);
                     if (cfg.resident) {
                         if (it == 0) ssf_mbar_wait(&w_full[ws], 0);
                     } else {
                         ssf_mbar_wait(&w_full[ws], (uint32_t)((g / cfg.nstage) & 1));
                     }
-                    ssf_mbar_wait(&a_ready[as], (uint32_t)((j >> 1) & 1));
+                    ssf_mbar_wait(&a_ready[as], (uint32_t)((j / SPW) & 1));
                     tc_fence_after();
                     // the descriptors of the 4 K-steps / hi-lo images differ only in the start-address field
                     const uint64_t w_hi = tc_smem_desc(ssf_smem_u32(sW + (size_t)ws * wchunk), lbo, 128);
@@ -321,11 +332,11 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                             for (int j = 0; j < 8; ++j) v[q][j] = act_apply(v[q][j] + bb[j], a.act1);
                         }
                     }
-                    // each warpgroup owns two of the four A stages and waits on them strictly in order (an mbarrier
+                    // each warpgroup owns SPW of the A stages and waits on them strictly in order (an mbarrier
                     // parity wait must never run more than one phase ahead of the barrier)
-                    const int j = (it / NPROD) * nk + kc, as = wg * 2 + (j & 1);
-                    if (j >= 2) {
-                        ssf_mbar_wait(&a_empty[as], (uint32_t)(((j >> 1) - 1) & 1));
+                    const int j = (it / NPROD) * nk + kc, as = wg * SPW + (j % SPW);
+                    if (j >= SPW) {
+                        ssf_mbar_wait(&a_empty[as], (uint32_t)(((j / SPW) - 1) & 1));
                         tc_fence_after();
                     }
                     const uint32_t t_hi = tmem + lane_base + a_col0 + as * 64;
@@ -347,6 +358,8 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
         const int r = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool need_dir = a.Wd2 != nullptr;
+        const int eg = (warp - W_EPI) >> 2;                            // epilogue warpgroup: columns [c_lo, c_hi) of the tile
+        const int c_lo = eg * (Nt / NEPI), c_hi = c_lo + Nt / NEPI;
         for (int it = 0; it < n_my; ++it) {
             const int db = it % cfg.nd;
             const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r;
@@ -366,7 +379,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             tc_fence_after();
             const uint32_t t_d = tmem + lane_base + (uint32_t)(db * Nt);
             float dot = 0.f;
-            for (int c = 0; c < Nt; c += 16) {
+            for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16];
                 tc_ld16(t_d + c, v);
                 tc_ld_wait();
@@ -399,11 +412,25 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], a.act);
                 if (a.epi_mode == SSF_EPI_STORE) {
-                    if (valid) {
-                        float* dst = a.y + row * a.ldy + cg;
+                    // A thread storing its own row would touch 32 different lines per instruction (the LSU request rate, not
+                    // bandwidth, then bounds the epilogue).  32 columns are staged in this warp's shared-memory tile and leave
+                    // as full 128-byte row segments, four rows per store instruction.
+                    float* et = sEpi + (warp - W_EPI) * (32 * STG_LD);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(et + lane * STG_LD + (c & 16) + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    if (c & 16) {
+                        __syncwarp();
+                        const int rg = lane >> 3, pc = lane & 7;
+                        const long long row0 = row - lane;     // first row of this warp's 32
+                        float* dst = a.y + (cg - 16) + pc * 4;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int rl = j * 4 + rg;
+                            if (row0 + rl < a.rows)
+                                *reinterpret_cast<float4*>(dst + (row0 + rl) * a.ldy) = *reinterpret_cast<const float4*>(et + rl * STG_LD + pc * 4);
+                        }
+                        __syncwarp();
                     }
                 } else if (a.epi_mode == SSF_EPI_MAX) {
                     // butterfly max over the S rows (= lanes) of a point; rows beyond `rows` only exist in the last tile
@@ -494,17 +521,21 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     cfg.nstage = cfg.resident ? cfg.nk : (int)(W_SMEM_MAX / wchunk);
     if (cfg.nstage > 16) cfg.nstage = 16;
     cfg.n_tiles = (int)((a.rows + 127) / 128);
+    { const char* e = getenv("SSF_W_SPLIT"); cfg.wsplit = e ? atoi(e) : 1; if (cfg.wsplit < 1 || cfg.wsplit > 16) cfg.wsplit = 1; }
     const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
-    const size_t smem_light = smem_fixed + (size_t)4 * 32 * STG_LD * 4, smem_heavy = smem_fixed + (size_t)8 * 32 * STG_LD * 4;
+    const size_t smem_light = smem_fixed + (size_t)8 * 32 * STG_LD * 4, smem_heavy = smem_fixed + (size_t)12 * 32 * STG_LD * 4;
     const int light_mode = dense_variant();
     // light_mode 1: only where it measured faster (pooled plain-row layers: the epilogue warps are the bottleneck and the
     // producers are cheap); 2: every eligible layer (tests)
     const bool light = light_mode && cfg.Nt <= 64 && cfg.resident && smem_light <= (size_t)LIGHT_SMEM_MAX &&
                        (light_mode == 2 || (a.epi_mode == SSF_EPI_MAX && a.a_mode == 0));
+    // 256-column tiles (single accumulator): two epilogue warpgroups (the DOT epilogue needs whole rows in one thread)
+    const bool wide = light_mode && cfg.Nt == 256 && a.epi_mode != SSF_EPI_DOT;
     cfg.nd = light ? 2 : ((2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIGHT_SMEM_MAX);
         if (e != cudaSuccess) return ssf_set_error(e);
         attr_set = true;
@@ -512,7 +543,8 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     const int n_cta = light ? 2 * 148 : 148;
     dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));
     if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem_light, (cudaStream_t)stream>>>(a, cfg);
-    else dense_tc_kernel<2><<<grid, DT_THREADS, smem_heavy, (cudaStream_t)stream>>>(a, cfg);
+    else if (wide) dense_tc_kernel<2><<<grid, DT_THREADS, smem_heavy, (cudaStream_t)stream>>>(a, cfg);
+    else dense_tc_kernel<0><<<grid, DT_THREADS, smem_heavy, (cudaStream_t)stream>>>(a, cfg);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

@@ -150,9 +150,13 @@ def test_dense_tc_grouped(B, Nsrc, Nq, S, K, N, epi):
 @pytest.mark.parametrize("rows,K,N,grouped,epi", [(148 * 128 * 7 + 33, 64, 64, False, 0), (148 * 128 * 5, 96, 64, False, 0),
                                                   (148 * 128 * 3 + 1, 128, 32, False, 0), (148 * 128 * 9 + 16, 64, 64, True, 1),
                                                   (148 * 128 * 4 + 64, 32, 64, True, 1), (128 * 40, 192, 64, False, 0),
-                                                  (148 * 128 * 6 + 48, 128, 64, True, 2), (100, 32, 32, False, 0)])
+                                                  (148 * 128 * 6 + 48, 128, 64, True, 2), (100, 32, 32, False, 0),
+                                                  # 256-column tiles: the two-epilogue-warpgroup variant
+                                                  (148 * 128 * 2 + 77, 256, 256, False, 0), (148 * 128 + 16, 128, 256, True, 1),
+                                                  (128 * 9, 256, 512, False, 0)])
 def test_dense_tc_light_variant_is_bit_identical(rows, K, N, grouped, epi):
-    """N <= 64 layers run the two-CTAs-per-SM variant by default; it must reproduce the one-CTA variant bit for bit."""
+    """The kernel variants (two CTAs per SM for N <= 64, two epilogue warpgroups for 256-column tiles) must reproduce the base
+    variant bit for bit."""
     from ssf_slam_b200 import functional as F_, tc
     g = torch.Generator().manual_seed(rows + K + N)
     r = lambda *s: torch.randn(*s, generator=g)

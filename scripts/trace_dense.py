@@ -1,0 +1,30 @@
+"""Developer tool (SSF_CV_TRACE=1 build): where a producer warp and an epilogue warp of dense_tc spend their cycles
+(CTA 0, clock64 deltas accumulated per phase), for plain-row layers `rows x K x N` given on the command line."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ssf_slam_b200 import functional as F_, tc, _native as nat
+
+L = nat.lib()
+L.ssf_dense_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
+buf = (ctypes.c_longlong * 48)()
+shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[1:]] or [(524288, 64, 64), (262144, 256, 256)]
+for rows, K, N in shapes:
+    X = torch.randn(rows, K, device="cuda")
+    img = tc.dense_image(torch.randn(N, K) / K ** 0.5).cuda()
+    b = torch.randn(N, device="cuda")
+    for _ in range(2):
+        F_.dense_tc(img, N, K, x1=X, bias=b, act=2)
+    torch.cuda.synchronize()
+    L.ssf_dense_trace_read(buf, 1)
+    F_.dense_tc(img, N, K, x1=X, bias=b, act=2)
+    torch.cuda.synchronize()
+    L.ssf_dense_trace_read(buf, 1)
+    t = list(buf)
+    tiles = -(-((rows + 127) // 128) // 148)     # tiles of CTA 0
+    chunks = tiles * (K // 32)
+    print("rows=%d K=%d N=%d: %d tiles, %d chunks in CTA 0" % (rows, K, N, tiles, chunks))
+    names = ["loop rest", "issue cp.async", "wait+read chunk", "first-layer math", "wait A stage", "split + st issue", "wait::st", "", "", "", "", "", "", "", "", "arrive"]
+    print("  producer (cycles per chunk): " + "  ".join("%s=%.0f" % (names[i], t[i] / chunks) for i in (0, 1, 2, 3, 4, 5, 6, 15)))
+    print("  epilogue (cycles per tile):  setup=%.0f  wait accumulator=%.0f  column loop=%.0f  arrive=%.0f" %
+          tuple(t[16 + i] / tiles / max(1, N // 256) for i in (0, 1, 2, 15)))

@@ -24,6 +24,16 @@
 #include "tc_common.cuh"
 #include "ssf_dense.h"
 
+#ifdef SSF_CV_TRACE
+// [role][event] accumulated cycles of CTA 0 (role 0: producer warp 0, 1: epilogue warp, 2: MMA warp); event 15 = count
+__device__ long long g_dt_trace[3 * 16];
+#define DTRACE_DECL long long tr_t = clock64(), tr_n
+#define DTRACE(role, ev) do { if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0) { tr_n = clock64(); atomicAdd((unsigned long long*)&g_dt_trace[(role) * 16 + (ev)], (unsigned long long)(tr_n - tr_t)); tr_t = tr_n; } } while (0)
+#else
+#define DTRACE_DECL
+#define DTRACE(role, ev) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int KC = 32;                    // K chunk
@@ -42,11 +52,21 @@ struct DenseCfg {
     int nd;          // accumulator buffers
     int n_tiles;     // row tiles
     int wsplit;      // bulk copies per streamed weight chunk
+    int pd;          // A chunks a producer warp keeps in flight ahead of the one it converts (ring of pd + 1 staging tiles)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async16_cg(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ssf_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ssf_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == 1) return fmaxf(v, 0.f);
     if (act == 2) return fmaxf(v, 0.1f * v);
@@ -114,8 +134,8 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
     uint64_t* d_full = bars + 40;                   // [2]
     uint64_t* d_empty = bars + 42;                  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
-    float* sStage = reinterpret_cast<float*>(bars + 46);   // [4 NPROD producer warps][32 rows][STG_LD]
-    float* sEpi = sStage + 4 * NPROD * (32 * STG_LD);      // [4 NEPI epilogue warps][32 rows][STG_LD]  (STORE epilogue)
+    float* sStage = reinterpret_cast<float*>(bars + 46);   // [4 NPROD producer warps][pd + 1 slots][32 rows][STG_LD]
+    float* sEpi = sStage + 4 * NPROD * (cfg.pd + 1) * (32 * STG_LD);   // [4 NEPI epilogue warps][32 rows][STG_LD]  (STORE epilogue)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == W_MMA) tc_alloc(tmem_slot, TCOLS);
@@ -226,6 +246,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
     } else if (warp < W_EPI) {
         // ---- A producers: warpgroup wg takes tiles it = wg, wg + 2, ...
         const int wg = warp >> 2;
+        DTRACE_DECL;
         const int r = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool grouped = a.S > 0 && a.idx != nullptr;
@@ -256,54 +277,83 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             }
             return c;
         };
-        // Coalesced loads: 8 lanes x 16 bytes cover the 128-byte K chunk of one row, 4 rows per instruction (a thread
-        // reading its own row would touch 32 different lines per instruction).  Lane l therefore fetches pieces of rows
-        // 4 j + (l >> 3); the chunk is transposed back to thread = row through this warp's shared-memory tile.
+        // Coalesced asynchronous loads: 8 lanes x 16 bytes cover the 128-byte K chunk of one row, 4 rows per instruction (a
+        // thread reading its own row would touch 32 different lines per instruction).  cp.async puts the pieces straight into
+        // this warp's ring of staging tiles, `pd` chunks ahead of the chunk being converted (no registers held by loads in
+        // flight); the chunk is then read back with thread = row.  The prefetch pointer runs through the same (tile, chunk)
+        // sequence as the conversion loop below, with its own copy of the row indices.
         const int rg = lane >> 3, pc = lane & 7;
-        float* stg = sStage + warp * (32 * STG_LD);
-        auto issue_loads = [&](const RowCtx& c, int kc, float4 (&v)[8]) {
-            const int k0 = kc * KC;
-            const int my = a.a_mode == 0 ? (int)c.rowc : (int)c.srow;   // row index in the source array (fits 31 bits)
-            const float* base;
-            long long ld;
-            if (a.a_mode == 0) {
-                if (k0 < a.c1) { base = a.x1 + k0; ld = a.ld1; } else { base = a.x2 + (k0 - a.c1); ld = a.ld2; }
-            } else {
-                base = a.G + a.offG + k0;
-                ld = a.ldG;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rrow = __shfl_sync(0xffffffffu, my, j * 4 + rg);
-                v[j] = __ldg(reinterpret_cast<const float4*>(base + (long long)rrow * ld + pc * 4));
-            }
+        const int PD = cfg.pd, D = PD + 1;
+        float* stg = sStage + warp * D * (32 * STG_LD);
+        const int total_n = wg < n_my ? ((n_my - wg + NPROD - 1) / NPROD) * nk : 0;
+        auto my_of = [&](int t, int id) -> int {   // row of this thread in the source array for the warpgroup's t-th tile
+            const int it = wg + t * NPROD;
+            const long long rowc = clampr(row_of(it < n_my ? it : n_my - 1));
+            if (a.a_mode == 0) return (int)rowc;
+            const long long pt = rowc / a.S;
+            return (int)((pt / a.Nq) * a.Nsrc + id);
         };
-        auto transpose_in = [&](const float4 (&vin)[8], float (&v)[4][8]) {
+        int pf_n = 0, pf_t = 0, pf_kc = 0;
+        int my_pf = my_of(0, load_idx(wg));
+        int idx_nx = load_idx(wg + NPROD);
+        auto issue_next = [&]() {   // cp.async of the next chunk of the sequence (if any) + one commit group, always
+            if (pf_n < total_n) {
+                const int k0 = pf_kc * KC;
+                const float* base;
+                long long ld;
+                if (a.a_mode == 0) {
+                    if (k0 < a.c1) { base = a.x1 + k0; ld = a.ld1; } else { base = a.x2 + (k0 - a.c1); ld = a.ld2; }
+                } else {
+                    base = a.G + a.offG + k0;
+                    ld = a.ldG;
+                }
+                float* dst = stg + (pf_n % D) * (32 * STG_LD) + pc * 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + (j * 4 + rg) * STG_LD + pc * 4) = vin[j];
+                for (int j = 0; j < 8; ++j) {
+                    const int rrow = __shfl_sync(0xffffffffu, my_pf, j * 4 + rg);
+                    const float* src = base + (long long)rrow * ld + pc * 4;
+                    if (a.a_mode == 0) cp_async16_cg(dst + (j * 4 + rg) * STG_LD, src);   // streamed once
+                    else cp_async16_ca(dst + (j * 4 + rg) * STG_LD, src);                 // gathered rows are re-used by neighbours
+                }
+                if (++pf_kc == nk) {
+                    pf_kc = 0;
+                    ++pf_t;
+                    my_pf = my_of(pf_t, idx_nx);
+                    idx_nx = load_idx(wg + (pf_t + 1) * NPROD);
+                }
+            }
+            ++pf_n;
+            cp_async_commit();
+        };
+        auto take_chunk = [&](int n, float (&v)[4][8]) {   // waits for chunk n of the sequence, reads this thread's row
+            if (PD == 1) cp_async_wait<1>();
+            else cp_async_wait<2>();
             __syncwarp();
+            const float* src = stg + (n % D) * (32 * STG_LD) + lane * STG_LD;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) lds8(stg + lane * STG_LD + q * 8, v[q]);
-            __syncwarp();
+            for (int q = 0; q < 4; ++q) lds8(src + q * 8, v[q]);
+            __syncwarp();   // the slot is overwritten by the cp.async issued for chunk n + D in the next step
         };
 
         if (wg < n_my) {
             RowCtx cur, nxt;
             int idx2;   // neighbour index two tiles (of this warpgroup) ahead
             float v[4][8];
-            float4 vn[8];
             nxt = make_ctx(wg, load_idx(wg));
             idx2 = load_idx(wg + NPROD);
-            issue_loads(nxt, 0, vn);
+            for (int m = 0; m < PD; ++m) issue_next();
+            int n_seq = 0;
             for (int it = wg; it < n_my; it += NPROD) {
                 cur = nxt;
                 nxt = make_ctx(it + NPROD, idx2);   // positions of the next tile: in flight while this tile is processed
                 idx2 = load_idx(it + 2 * NPROD);
                 const float dx = cur.px - cur.qx, dy = cur.py - cur.qy, dz = cur.pz - cur.qz;
                 for (int kc = 0; kc < nk; ++kc) {
-                    transpose_in(vn, v);
-                    if (kc + 1 < nk) issue_loads(cur, kc + 1, vn);
-                    else if (it + NPROD < n_my) issue_loads(nxt, 0, vn);
+                    DTRACE(0, 0);   // rest of the loop body (previous arrive .. here)
+                    issue_next();
+                    DTRACE(0, 1);   // cp.async issue of the chunk `pd` ahead
+                    take_chunk(n_seq++, v);
+                    DTRACE(0, 2);   // wait for this chunk + read back with thread = row
                     const int k0 = kc * KC;
                     if (a.a_mode == 1) {
                         if (a.H != nullptr) {
@@ -335,10 +385,12 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                     // each warpgroup owns SPW of the A stages and waits on them strictly in order (an mbarrier
                     // parity wait must never run more than one phase ahead of the barrier)
                     const int j = (it / NPROD) * nk + kc, as = wg * SPW + (j % SPW);
+                    DTRACE(0, 3);   // first-layer math
                     if (j >= SPW) {
                         ssf_mbar_wait(&a_empty[as], (uint32_t)(((j / SPW) - 1) & 1));
                         tc_fence_after();
                     }
+                    DTRACE(0, 4);   // wait for the A stage
                     const uint32_t t_hi = tmem + lane_base + a_col0 + as * 64;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -347,9 +399,12 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                         tc_st8(t_hi + q * 8, hi);
                         tc_st8(t_hi + 32 + q * 8, lo);
                     }
+                    DTRACE(0, 5);   // split + tcgen05.st issue
                     tc_st_wait();
+                    DTRACE(0, 6);   // tcgen05.wait::st
                     tc_fence_before();
                     mbar_arrive(&a_ready[as]);
+                    DTRACE(0, 15);
                 }
             }
         }
@@ -358,6 +413,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
         const int r = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool need_dir = a.Wd2 != nullptr;
+        DTRACE_DECL;
         const int eg = (warp - W_EPI) >> 2;                            // epilogue warpgroup: columns [c_lo, c_hi) of the tile
         const int c_lo = eg * (Nt / NEPI), c_hi = c_lo + Nt / NEPI;
         for (int it = 0; it < n_my; ++it) {
@@ -375,8 +431,10 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 dy = __ldg(ps + 1) - __ldg(pq + 1);
                 dz = __ldg(ps + 2) - __ldg(pq + 2);
             }
+            DTRACE(1, 0);   // row setup
             ssf_mbar_wait(&d_full[db], (uint32_t)((it / cfg.nd) & 1));
             tc_fence_after();
+            DTRACE(1, 1);   // wait for the accumulator
             const uint32_t t_d = tmem + lane_base + (uint32_t)(db * Nt);
             float dot = 0.f;
             for (int c = c_lo; c < c_hi; c += 16) {
@@ -468,9 +526,11 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                     }
                 }
             }
+            DTRACE(1, 2);   // column loop
             tc_fence_before();
             mbar_arrive(&d_empty[db]);
             if (a.epi_mode == SSF_EPI_DOT && valid) a.y[row] = dot + a.b0;
+            DTRACE(1, 15);
         }
     }
     tc_fence_before();
@@ -493,6 +553,14 @@ extern "C" int ssf_dense_set_variant(int light) {
     g_dense_variant = light < 0 ? 0 : (light > 2 ? 2 : light);
     return prev;
 }
+
+#ifdef SSF_CV_TRACE
+extern "C" int ssf_dense_trace_read(long long* out, int reset) {
+    if (cudaMemcpyFromSymbol(out, g_dt_trace, sizeof(long long) * 48) != cudaSuccess) return 2;
+    if (reset) { long long z[48] = {0}; cudaMemcpyToSymbol(g_dt_trace, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int ssf_dense_args_bytes(void) { return (int)sizeof(ssf_dense_args); }
 
@@ -523,14 +591,17 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     cfg.n_tiles = (int)((a.rows + 127) / 128);
     { const char* e = getenv("SSF_W_SPLIT"); cfg.wsplit = e ? atoi(e) : 1; if (cfg.wsplit < 1 || cfg.wsplit > 16) cfg.wsplit = 1; }
     const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
-    const size_t smem_light = smem_fixed + (size_t)8 * 32 * STG_LD * 4, smem_heavy = smem_fixed + (size_t)12 * 32 * STG_LD * 4;
+    const size_t tile_b = (size_t)32 * STG_LD * 4;   // one staging tile of a warp
     const int light_mode = dense_variant();
     // light_mode 1: only where it measured faster (pooled plain-row layers: the epilogue warps are the bottleneck and the
     // producers are cheap); 2: every eligible layer (tests)
+    const size_t smem_light = smem_fixed + (4 * 2 + 4) * tile_b;   // prefetch depth 1 at least
     const bool light = light_mode && cfg.Nt <= 64 && cfg.resident && smem_light <= (size_t)LIGHT_SMEM_MAX &&
                        (light_mode == 2 || (a.epi_mode == SSF_EPI_MAX && a.a_mode == 0));
     // 256-column tiles (single accumulator): two epilogue warpgroups (the DOT epilogue needs whole rows in one thread)
-    const bool wide = light_mode && cfg.Nt == 256 && a.epi_mode != SSF_EPI_DOT;
+    // ... and for plain-row layers of >= 64 columns, whose single producer warpgroup keeps up (measured: 8-25 % faster; the
+    // grouped first layer needs both producer warpgroups)
+    const bool wide = light_mode && !light && a.epi_mode != SSF_EPI_DOT && (cfg.Nt == 256 || (a.a_mode == 0 && cfg.Nt >= 64));
     cfg.nd = light ? 2 : ((2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1);
     static bool attr_set = false;
     if (!attr_set) {
@@ -542,9 +613,24 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     }
     const int n_cta = light ? 2 * 148 : 148;
     dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));
-    if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem_light, (cudaStream_t)stream>>>(a, cfg);
-    else if (wide) dense_tc_kernel<2><<<grid, DT_THREADS, smem_heavy, (cudaStream_t)stream>>>(a, cfg);
-    else dense_tc_kernel<0><<<grid, DT_THREADS, smem_heavy, (cudaStream_t)stream>>>(a, cfg);
+    // shared-memory plan: staging tiles (producer rings with 1 or 2 chunks in flight + the STORE epilogue tiles), then the
+    // weight image: resident when it fits in what is left (at most W_SMEM_MAX), else a ring of whole chunks
+    const int n_pw = (light || wide) ? 4 : 8, n_ew = wide ? 8 : 4;
+    const size_t smem_cap = light ? (size_t)LIGHT_SMEM_MAX : (size_t)227 * 1024;
+    const size_t smem_par = (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
+    size_t w_budget = smem_cap - smem_par - ((size_t)n_pw * 2 + n_ew) * tile_b;
+    if (w_budget > (size_t)W_SMEM_MAX) w_budget = W_SMEM_MAX;
+    cfg.resident = (size_t)cfg.nk * wchunk <= w_budget;
+    cfg.nstage = cfg.resident ? cfg.nk : (int)(w_budget / wchunk);
+    if (cfg.nstage > 16) cfg.nstage = 16;
+    if (cfg.nstage < 1) return ssf_arg_error("dense_tc: shared-memory budget exceeded");
+    const size_t smem_w = (size_t)cfg.nstage * wchunk + smem_par;
+    cfg.pd = 2;
+    while (cfg.pd > 1 && smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b > smem_cap) --cfg.pd;
+    const size_t smem = smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b;
+    if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem, (cudaStream_t)stream>>>(a, cfg);
+    else if (wide) dense_tc_kernel<2><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
+    else dense_tc_kernel<0><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

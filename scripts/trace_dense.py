@@ -28,3 +28,5 @@ for rows, K, N in shapes:
     print("  producer (cycles per chunk): " + "  ".join("%s=%.0f" % (names[i], t[i] / chunks) for i in (0, 1, 2, 3, 4, 5, 6, 15)))
     print("  epilogue (cycles per tile):  setup=%.0f  wait accumulator=%.0f  column loop=%.0f  arrive=%.0f" %
           tuple(t[16 + i] / tiles / max(1, N // 256) for i in (0, 1, 2, 15)))
+    print("    column loop per tile: tail=%.0f  tcgen05.ld+wait=%.0f  math=%.0f  staging stores=%.0f  row-segment stores=%.0f" %
+          tuple(t[16 + i] / tiles / max(1, N // 256) for i in (3, 4, 5, 6, 7)))

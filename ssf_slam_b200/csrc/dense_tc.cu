@@ -39,6 +39,7 @@ namespace {
 constexpr int KC = 32;                    // K chunk
 constexpr int AS = 4;                     // TMEM A stages (64 columns each: hi | lo)
 constexpr int DT_THREADS = 448;           // heavy variant: 2 producer warpgroups, 1 CTA per SM
+constexpr int DT_THREADS_FULL = 576;      // full variant: 2 producer + 2 epilogue warpgroups (96 registers per thread)
 constexpr int DT_THREADS_LIGHT = 288;     // light variant: 1 producer warpgroup, 2 CTAs per SM (small layers)
 constexpr int W_SMEM_MAX = 150 * 1024;    // bytes of shared memory for weight images
 constexpr int LIGHT_SMEM_MAX = 112 * 1024; // per-CTA shared memory of the light variant (two CTAs per SM)
@@ -102,17 +103,19 @@ struct RowCtx {
 // VARIANT 1 (light): for layers whose weight image is small: one producer warpgroup, 288 threads, 256 TMEM columns, <= 112 KB
 //                    shared memory -> two CTAs per SM, i.e. two independent tile pipelines (the MMA warp also fetches the
 //                    resident weights).
+// VARIANT 3 (full):  two producer and two epilogue warpgroups (576 threads, 96 registers): grouped layers with a small weight
+//                    image, where the gather needs both producer warpgroups and the pooling epilogue is the bottleneck.
 // VARIANT 2 (wide):  for 256-column tiles, whose accumulator cannot be double buffered (the epilogue and the next tile's MMAs
 //                    serialise): one producer warpgroup with all four A stages and TWO epilogue warpgroups, each draining
 //                    half of the columns.
 template <int VARIANT>
-__global__ void __launch_bounds__(VARIANT == 1 ? DT_THREADS_LIGHT : DT_THREADS, VARIANT == 1 ? 2 : 1)
+__global__ void __launch_bounds__(VARIANT == 1 ? DT_THREADS_LIGHT : (VARIANT == 3 ? DT_THREADS_FULL : DT_THREADS), VARIANT == 1 ? 2 : 1)
 dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
-    constexpr int NPROD = VARIANT == 0 ? 2 : 1;   // producer warpgroups
-    constexpr int NEPI = VARIANT == 2 ? 2 : 1;    // epilogue warpgroups
-    constexpr int SPW = VARIANT == 2 ? 4 : 2;     // A stages per producer warpgroup
-    constexpr int NTHR = VARIANT == 1 ? DT_THREADS_LIGHT : DT_THREADS;
-    constexpr int W_EPI = 4 * NPROD;              // first epilogue warp
+    constexpr int NPROD = (VARIANT == 0 || VARIANT == 3) ? 2 : 1;   // producer warpgroups
+    constexpr int NEPI = VARIANT >= 2 ? 2 : 1;                      // epilogue warpgroups
+    constexpr int SPW = VARIANT == 2 ? 4 : 2;                       // A stages per producer warpgroup
+    constexpr int NTHR = VARIANT == 1 ? DT_THREADS_LIGHT : (VARIANT == 3 ? DT_THREADS_FULL : DT_THREADS);
+    constexpr int W_EPI = 4 * NPROD;                                // first epilogue warp
     constexpr int W_MMA = W_EPI + 4 * NEPI, W_TMA = VARIANT == 1 ? W_MMA : W_MMA + 1;
     constexpr uint32_t TCOLS = VARIANT == 1 ? 256 : 512;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -439,8 +442,10 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             float dot = 0.f;
             for (int c = c_lo; c < c_hi; c += 16) {
                 float v[16];
+                DTRACE(1, 3);   // previous iteration's tail
                 tc_ld16(t_d + c, v);
                 tc_ld_wait();
+                DTRACE(1, 4);   // tcgen05.ld + wait
                 const int cg = n0 + c;   // global output column
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -469,6 +474,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], a.act);
+                DTRACE(1, 5);   // bias / per-point / direction terms, activation
                 if (a.epi_mode == SSF_EPI_STORE) {
                     // A thread storing its own row would touch 32 different lines per instruction (the LSU request rate, not
                     // bandwidth, then bounds the epilogue).  32 columns are staged in this warp's shared-memory tile and leave
@@ -477,6 +483,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<float4*>(et + lane * STG_LD + (c & 16) + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    DTRACE(1, 6);   // staging stores
                     if (c & 16) {
                         __syncwarp();
                         const int rg = lane >> 3, pc = lane & 7;
@@ -489,6 +496,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                                 *reinterpret_cast<float4*>(dst + (row0 + rl) * a.ldy) = *reinterpret_cast<const float4*>(et + rl * STG_LD + pc * 4);
                         }
                         __syncwarp();
+                        DTRACE(1, 7);   // coalesced row-segment stores
                     }
                 } else if (a.epi_mode == SSF_EPI_MAX) {
                     // butterfly max over the S rows (= lanes) of a point; rows beyond `rows` only exist in the last tile
@@ -607,6 +615,7 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIGHT_SMEM_MAX);
         if (e != cudaSuccess) return ssf_set_error(e);
         attr_set = true;
@@ -615,7 +624,13 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));
     // shared-memory plan: staging tiles (producer rings with 1 or 2 chunks in flight + the STORE epilogue tiles), then the
     // weight image: resident when it fits in what is left (at most W_SMEM_MAX), else a ring of whole chunks
-    const int n_pw = (light || wide) ? 4 : 8, n_ew = wide ? 8 : 4;
+    static int full_mode = -1;
+    if (full_mode < 0) { const char* e = getenv("SSF_DENSE_FULL"); full_mode = e ? atoi(e) : 1; }
+    const size_t smem_full = smem_fixed + (size_t)(8 * 2 + 8) * tile_b;
+    // (measured: the SA / SU pooling layers gain 4-8 %; layers that also add a per-point block H lose under the 96-register cap)
+    const bool full = light_mode && full_mode && !light && !wide && a.a_mode == 1 && a.H == nullptr && a.epi_mode != SSF_EPI_DOT && cfg.Nt >= 64 &&
+                      cfg.Nt <= 128 && cfg.resident && smem_full <= (size_t)227 * 1024;
+    const int n_pw = (light || wide) ? 4 : 8, n_ew = (wide || full) ? 8 : 4;
     const size_t smem_cap = light ? (size_t)LIGHT_SMEM_MAX : (size_t)227 * 1024;
     const size_t smem_par = (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
     size_t w_budget = smem_cap - smem_par - ((size_t)n_pw * 2 + n_ew) * tile_b;
@@ -629,6 +644,7 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     while (cfg.pd > 1 && smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b > smem_cap) --cfg.pd;
     const size_t smem = smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b;
     if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem, (cudaStream_t)stream>>>(a, cfg);
+    else if (full) dense_tc_kernel<3><<<grid, DT_THREADS_FULL, smem, (cudaStream_t)stream>>>(a, cfg);
     else if (wide) dense_tc_kernel<2><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
     else dense_tc_kernel<0><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
     ssf_count_launch();

@@ -192,3 +192,31 @@ def test_dense_tc_light_variant_is_bit_identical(rows, K, N, grouped, epi):
         ref = (D.max(dim=1).values if epi == 1 else D @ wv.cpu().double() + 0.5)[None]
     assert y_light.shape == ref.shape
     assert float((y_light.cpu().double() - ref).abs().max()) < 3e-6 * max(1.0, float(ref.abs().max()))
+
+
+def test_dense_tc_full_variant_grouped_without_point_block():
+    """Grouped pooling layer without a per-point block H (the SA / SU layers): runs the 2 + 2 warpgroup variant by default; must
+    equal the base variant bit for bit and the fp64 definition."""
+    from ssf_slam_b200 import functional as F_, tc
+    g = torch.Generator().manual_seed(5)
+    r = lambda *s: torch.randn(*s, generator=g)
+    B, Nsrc, Nq, S, K, N = 2, 900, 148 * 8 * 3 + 5, 16, 64, 64
+    G, b1, Wd1, ps, pq = r(B, Nsrc, K), r(K), r(3, K) * 0.3, r(B, Nsrc, 3), r(B, Nq, 3)
+    idx = torch.randint(0, Nsrc, (B, Nq, S), generator=g, dtype=torch.int32)
+    W, bias = r(N, K) / K ** 0.5, r(N)
+    cu = lambda t: t.cuda().contiguous()
+    img = cu(tc.dense_image(W))
+    args = dict(G=cu(G), b1=cu(b1), Wd1=cu(Wd1), act1=1, idx=cu(idx), pos_src=cu(ps), pos_q=cu(pq), bias=cu(bias), act=1, epi=1)
+    prev = F_.set_dense_variant(1)
+    try:
+        y1 = F_.dense_tc(img, N, K, **args)
+        F_.set_dense_variant(0)
+        y0 = F_.dense_tc(img, N, K, **args)
+    finally:
+        F_.set_dense_variant(prev)
+    assert torch.equal(y1, y0)
+    li, bi = idx.long(), torch.arange(B)[:, None, None]
+    dirs = (ps[bi, li] - pq[:, :, None, :]).double()
+    A = _act(G[bi, li].double() + b1.double() + dirs @ Wd1.double(), 1)
+    ref = _act(A @ W.double().t() + bias.double(), 1).max(dim=2).values
+    assert float((y1.cpu().double() - ref).abs().max()) < 3e-6 * max(1.0, float(ref.abs().max()))

@@ -440,13 +440,9 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             DTRACE(1, 1);   // wait for the accumulator
             const uint32_t t_d = tmem + lane_base + (uint32_t)(db * Nt);
             float dot = 0.f;
-            for (int c = c_lo; c < c_hi; c += 16) {
-                float v[16];
-                DTRACE(1, 3);   // previous iteration's tail
-                tc_ld16(t_d + c, v);
-                tc_ld_wait();
-                DTRACE(1, 4);   // tcgen05.ld + wait
-                const int cg = n0 + c;   // global output column
+            // bias, per-point rows, direction term and activation on 16 accumulator columns starting at tile column c
+            auto finish16 = [&](int c, float (&v)[16]) {
+                const int cg = n0 + c;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 bb = *reinterpret_cast<const float4*>(sBias + c + q * 4);
@@ -474,31 +470,49 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], a.act);
-                DTRACE(1, 5);   // bias / per-point / direction terms, activation
-                if (a.epi_mode == SSF_EPI_STORE) {
-                    // A thread storing its own row would touch 32 different lines per instruction (the LSU request rate, not
-                    // bandwidth, then bounds the epilogue).  32 columns are staged in this warp's shared-memory tile and leave
-                    // as full 128-byte row segments, four rows per store instruction.
-                    float* et = sEpi + (warp - W_EPI) * (32 * STG_LD);
+            };
+            if (a.epi_mode == SSF_EPI_STORE) {
+                // A thread storing its own row would touch 32 different lines per instruction (the LSU request rate, not
+                // bandwidth, then bounds the epilogue).  32 columns per step: two TMEM loads in flight, the values are staged in
+                // this warp's shared-memory tile and leave as full 128-byte row segments, four rows per store instruction.
+                float* et = sEpi + (warp - W_EPI) * (32 * STG_LD);
+                const int rg = lane >> 3, pc = lane & 7;
+                const long long row0 = row - lane;     // first row of this warp's 32
+                for (int c = c_lo; c < c_hi; c += 32) {
+                    float va[16], vb[16];
+                    DTRACE(1, 3);   // previous iteration's tail
+                    tc_ld16(t_d + c, va);
+                    tc_ld16(t_d + c + 16, vb);
+                    tc_ld_wait();
+                    DTRACE(1, 4);   // tcgen05.ld + wait
+                    finish16(c, va);
+                    finish16(c + 16, vb);
+                    DTRACE(1, 5);   // bias / per-point / direction terms, activation
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<float4*>(et + lane * STG_LD + (c & 16) + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                    DTRACE(1, 6);   // staging stores
-                    if (c & 16) {
-                        __syncwarp();
-                        const int rg = lane >> 3, pc = lane & 7;
-                        const long long row0 = row - lane;     // first row of this warp's 32
-                        float* dst = a.y + (cg - 16) + pc * 4;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int rl = j * 4 + rg;
-                            if (row0 + rl < a.rows)
-                                *reinterpret_cast<float4*>(dst + (row0 + rl) * a.ldy) = *reinterpret_cast<const float4*>(et + rl * STG_LD + pc * 4);
-                        }
-                        __syncwarp();
-                        DTRACE(1, 7);   // coalesced row-segment stores
+                    for (int q = 0; q < 4; ++q) {
+                        *reinterpret_cast<float4*>(et + lane * STG_LD + q * 4) = make_float4(va[q * 4], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
+                        *reinterpret_cast<float4*>(et + lane * STG_LD + 16 + q * 4) = make_float4(vb[q * 4], vb[q * 4 + 1], vb[q * 4 + 2], vb[q * 4 + 3]);
                     }
-                } else if (a.epi_mode == SSF_EPI_MAX) {
+                    DTRACE(1, 6);   // staging stores
+                    __syncwarp();
+                    float* dst = a.y + (n0 + c) + pc * 4;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int rl = j * 4 + rg;
+                        if (row0 + rl < a.rows)
+                            *reinterpret_cast<float4*>(dst + (row0 + rl) * a.ldy) = *reinterpret_cast<const float4*>(et + rl * STG_LD + pc * 4);
+                    }
+                    __syncwarp();
+                    DTRACE(1, 7);   // coalesced row-segment stores
+                }
+            } else
+            for (int c = c_lo; c < c_hi; c += 16) {
+                float v[16];
+                tc_ld16(t_d + c, v);
+                tc_ld_wait();
+                const int cg = n0 + c;   // global output column
+                finish16(c, v);
+                if (a.epi_mode == SSF_EPI_MAX) {
                     // butterfly max over the S rows (= lanes) of a point; rows beyond `rows` only exist in the last tile
                     // and belong to no stored point (rows % S == 0)
                     if (a.S == 16) {   // 16 values over 16 lanes: lane s ends up with column c + s

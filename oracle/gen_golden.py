@@ -66,6 +66,32 @@ def _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels):
     print("%s: reference == port (bit-exact); |flow|max %.4f" % (name, float(flows[0].abs().max())))
 
 
+def gen_tflow_afterpc(n_points, data_seed, weight_seed=0):
+    """The 4-channel INPUT variant: the unmodified ``TFlowV3_Occlussion_addSeg_afterPC.TFlow`` (first layer Conv1d(4, 32)),
+    called as its driver does with ``[xyz | label]`` features."""
+    TFlow = import_reference_tflow("TFlowV3_Occlussion_addSeg_afterPC")
+    sd = tflow_port.random_init_state_dict(weight_seed, 3, input_channels=4)
+    net = TFlow().eval()
+    net.load_state_dict(sd, strict=True)
+    item = synth.make_pair(data_seed, n_points)
+    pc1 = torch.from_numpy(item["pos1"].T.copy()).unsqueeze(0)
+    pc2 = torch.from_numpy(item["pos2"].T.copy()).unsqueeze(0)
+    lab1 = torch.from_numpy(item["s_fg_mask"].astype(np.float32))[None, None]
+    lab2 = torch.from_numpy(item["t_fg_mask"].astype(np.float32))[None, None]
+    f1, f2 = torch.cat([pc1, lab1], dim=1), torch.cat([pc2, lab2], dim=1)
+    with torch.no_grad():
+        flows, fps = net(pc1, pc2, f1, f2)
+    pflows, pfps = tflow_port.tflow_forward(sd, pc1, pc2, feats1=f1, feats2=f2)
+    for a, b in zip(list(flows) + list(fps), list(pflows) + list(pfps)):
+        assert torch.equal(a, b), "oracle port deviates from the reference (afterPC variant)"
+    name = "tflow_afterpc_n%d.npz" % n_points
+    np.savez_compressed(os.path.join(OUT, name), pos1=item["pos1"], pos2=item["pos2"], lab1=lab1[0, 0].numpy(), lab2=lab2[0, 0].numpy(),
+                        flow0=flows[0][0].numpy(), flow1=flows[1][0].numpy(), flow2=flows[2][0].numpy(),
+                        flow3=flows[3][0].numpy(), fps1=fps[0][0].numpy(), fps2=fps[1][0].numpy(), fps3=fps[2][0].numpy(),
+                        weight_seed=weight_seed, data_seed=data_seed)
+    print("%s: reference == port (bit-exact); |flow|max %.4f" % (name, float(flows[0].abs().max())))
+
+
 def _reference_solve_rt():
     path = "/root/reference/scripts/PointCloudOdometry.py"
     tree = ast.parse(open(path).read())
@@ -144,3 +170,4 @@ if __name__ == "__main__":
     gen_tflow(2048, data_seed=42)
     gen_tflow(8192, data_seed=0)
     gen_tflow(2048, data_seed=43, flow_channels=4)
+    gen_tflow_afterpc(2048, data_seed=44)

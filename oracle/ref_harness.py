@@ -16,8 +16,8 @@ def reference_available():
     return os.path.isfile(os.path.join(REF_ASF, "TFlowV3_Occlussion.py"))
 
 
-def import_reference_tflow():
-    """Returns the reference's ``TFlow`` class (unmodified source, executed on CPU)."""
+def import_reference_tflow(module="TFlowV3_Occlussion"):
+    """Returns the reference's ``TFlow`` class (unmodified source, executed on CPU) from the given model file."""
     if not reference_available():
         raise RuntimeError("reference tree not mounted at " + REF_ASF)
     sys.dont_write_bytecode = True  # the mount is read-only
@@ -26,5 +26,5 @@ def import_reference_tflow():
     for p in (REF_ASF, os.path.join(here, "shims"), root):
         if p not in sys.path:
             sys.path.insert(0, p)
-    import TFlowV3_Occlussion as ref  # noqa: E402
-    return ref.TFlow
+    import importlib
+    return importlib.import_module(module).TFlow

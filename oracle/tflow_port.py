@@ -229,15 +229,17 @@ SA_CFG = [("sa1", 2048, 16), ("sa2", 512, 16), ("sa3", 256, 16), ("sa4", 128, 8)
 
 
 @torch.no_grad()
-def tflow_forward(sd, pc1, pc2, return_intermediates=False):
-    """TFlow.forward, ASF/TFlowV3_Occlussion.py:105-196.  pc1, pc2: f32 [B,3,N] on CPU."""
+def tflow_forward(sd, pc1, pc2, return_intermediates=False, feats1=None, feats2=None):
+    """TFlow.forward, ASF/TFlowV3_Occlussion.py:105-196.  pc1, pc2: f32 [B,3,N] on CPU.  feats1, feats2 [B,C,N]: the optional
+    input features (used only when both are given, :111-116; C = 4 for TFlowV3_Occlussion_addSeg_afterPC.py:68)."""
     sd = {k: v for k, v in sd.items()}
     inter = {}
 
     def point_conv(x):
         return leaky_conv1d(sd, "point_conv.1", leaky_conv1d(sd, "point_conv.0", x))
 
-    pcs1, pcs2, f1, f2, fps = [pc1], [pc2], [point_conv(pc1)], [point_conv(pc2)], []
+    in1, in2 = (pc1, pc2) if feats1 is None or feats2 is None else (feats1, feats2)
+    pcs1, pcs2, f1, f2, fps = [pc1], [pc2], [point_conv(in1)], [point_conv(in2)], []
     for prefix, npoint, nsample in SA_CFG:
         x, f, i = set_abstraction(sd, prefix, npoint, nsample, pcs1[-1], f1[-1])
         pcs1.append(x), f1.append(f), fps.append(i)

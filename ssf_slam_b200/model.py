@@ -489,12 +489,16 @@ class TFlow(nn.Module):
 
     SA = (("sa1", 2048, 16), ("sa2", 512, 16), ("sa3", 256, 16), ("sa4", 128, 8))
 
-    def __init__(self, npoint=8192, add_seg_after_flow=False):
+    def __init__(self, npoint=8192, add_seg_after_flow=False, input_channels=3):
         """``add_seg_after_flow`` is the reference's source-level flag ``add_Seg_after_FLow`` (utils/datasets/carla.py:9):
-        4-channel flow heads whose last channel is a segmentation logit; shipped default False."""
+        4-channel flow heads whose last channel is a segmentation logit; shipped default False.
+        ``input_channels=4`` is ``TFlowV3_Occlussion_addSeg_afterPC.TFlow`` (its only difference: ``Conv1d(4, 32)`` as the first
+        layer, ASF/TFlowV3_Occlussion_addSeg_afterPC.py:68), fed through ``forward(pc1, pc2, feats1, feats2)`` with
+        ``[B,4,N]`` features (xyz + a per-point label)."""
         super().__init__()
         fc_ch = 4 if add_seg_after_flow else 3
-        self.point_conv = nn.Sequential(_LeakyConv1d(3, 32, bias=False), _LeakyConv1d(32, 32, bias=False))
+        self.input_channels = input_channels
+        self.point_conv = nn.Sequential(_LeakyConv1d(input_channels, 32, bias=False), _LeakyConv1d(32, 32, bias=False))
         self.sa1 = PointNetSetAbstraction(2048, 0.5, 16, 32, [32, 32, 64])
         self.sa2 = PointNetSetAbstraction(512, 2.0, 16, 64, [64, 64, 128])
         self.sa3 = PointNetSetAbstraction(256, 4.0, 16, 128, [128, 128, 256])
@@ -527,14 +531,19 @@ class TFlow(nn.Module):
         return self._prepared[1]
 
     @torch.no_grad()
-    def forward_pm(self, xyz1, xyz2):
-        """xyz1, xyz2 f32 [B,N,3] (point-major, CUDA) -> (flows pm [[B,N,3],[B,2048,3],[B,512,3],[B,256,3]], fps idx x3)."""
+    def forward_pm(self, xyz1, xyz2, f1=None, f2=None):
+        """xyz1, xyz2 f32 [B,N,3] (point-major, CUDA) -> (flows pm [[B,N,3],[B,2048,3],[B,512,3],[B,256,3]], fps idx x3).
+        f1, f2 f32 [B,N,input_channels]: the optional input features of the reference's forward (TFlowV3_Occlussion.py:111-116:
+        ``point_conv`` runs on them instead of the coordinates when BOTH are given)."""
         nat.require_device()
         F_.knn_cache_clear()
         W = self.weights(xyz1.device)
         B = xyz1.shape[0]
         xyz = [torch.cat([xyz1, xyz2], dim=0).contiguous()]  # both clouds as one batch of 2B
-        x = F_.linear(xyz[0], W["pc0"], 32, act=ACT_LEAKY)
+        x0 = xyz[0] if f1 is None or f2 is None else torch.cat([f1, f2], dim=0).contiguous()
+        if x0.shape[-1] != self.input_channels:
+            raise nat.SsfError("point_conv expects %d input channels, got %d" % (self.input_channels, x0.shape[-1]))
+        x = F_.linear(x0, W["pc0"], 32, act=ACT_LEAKY)
         feats = [F_.dense_tc(W["pc1_img"], 32, 32, x1=x, act=ACT_LEAKY) if _tc() else F_.linear(x, W["pc1"], 32, act=ACT_LEAKY)]
         fps = []
         for name, npoint, nsample in self.SA:
@@ -575,11 +584,14 @@ class TFlow(nn.Module):
 
     @torch.no_grad()
     def forward(self, pc1, pc2, feats1=None, feats2=None):
-        """Reference signature: pc1, pc2 f32 [B,3,N] CUDA -> ([4 flows B x3xn], [3 fps idx])."""
-        if feats1 is not None or feats2 is not None:
-            raise nat.SsfError("extra input features are not supported (the reference drivers never pass them)")
+        """Reference signature: pc1, pc2 f32 [B,3,N] CUDA (, feats1, feats2 f32 [B,C,N]) -> ([4 flows B x3xn], [3 fps idx]).
+        As in the reference, the features are used only when both are given (TFlowV3_Occlussion.py:111-116)."""
         nat.require_device()
         x1 = F_.transpose(pc1.contiguous().float())
         x2 = F_.transpose(pc2.contiguous().float())
-        flows, fps = self.forward_pm(x1, x2)
+        if feats1 is None or feats2 is None:
+            feats1 = feats2 = None
+        else:
+            feats1, feats2 = F_.transpose(feats1.contiguous().float()), F_.transpose(feats2.contiguous().float())
+        flows, fps = self.forward_pm(x1, x2, feats1, feats2)
         return [F_.transpose(f) for f in flows], fps

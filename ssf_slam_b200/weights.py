@@ -8,10 +8,11 @@ reference in oracle/gen_golden.py).  BatchNorm running statistics are non-trivia
 import torch
 
 
-def random_init_state_dict(seed=0, flow_channels=3):
+def random_init_state_dict(seed=0, flow_channels=3, input_channels=3):
     """State dict with the reference's key names and shapes, filled deterministically WITHOUT the
     reference (for the GPU box).  ``flow_channels=4`` gives the ``add_Seg_after_FLow=True`` variant's 4-channel flow
-    heads (ASF/utils/soflow.py:343-346).  NOT the reference's init distribution draw-for-draw: goldens that
+    heads (ASF/utils/soflow.py:343-346); ``input_channels=4`` the ``_afterPC`` variant's first layer
+    (ASF/TFlowV3_Occlussion_addSeg_afterPC.py:68).  NOT the reference's init distribution draw-for-draw: goldens that
     must match the reference use the state_dict saved by oracle/gen_golden.py instead."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
@@ -29,7 +30,7 @@ def random_init_state_dict(seed=0, flow_channels=3):
         sd[key + ".running_var"] = 1.0 + 0.2 * torch.rand(c, generator=g)
         sd[key + ".num_batches_tracked"] = torch.tensor(0)
 
-    conv("point_conv.0.composed_module.0", 32, 3, 1, False)
+    conv("point_conv.0.composed_module.0", 32, input_channels, 1, False)
     conv("point_conv.1.composed_module.0", 32, 32, 1, False)
     for name, cin, mlp in (("sa1", 32, [32, 32, 64]), ("sa2", 64, [64, 64, 128]),
                            ("sa3", 128, [128, 128, 256]), ("sa4", 256, [256, 256, 512])):

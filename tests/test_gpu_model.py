@@ -271,3 +271,32 @@ def test_tflow_four_channel_flow_heads_vs_reference_golden(golden_dir):
     assert flows[0].shape == (1, 4, 2048) and max(errs) <= FLOW_TOL
     out = SceneFlowFrontEnd(net, tau=0.10).process(g["pos1"][None], g["pos2"][None], return_flow=True)
     assert out["flow"].shape == (1, 2048, 4) and out["mask"].shape == (1, 2048)
+
+
+def test_tflow_four_channel_input_variant_vs_reference_golden(golden_dir):
+    """f-4: the `_afterPC` variant (first layer Conv1d(4, 32), called with [xyz | label] features); golden written by the
+    unmodified TFlowV3_Occlussion_addSeg_afterPC.TFlow: FPS indices exact, all four flow levels within 1e-4.  Also the base
+    model's feats1 / feats2 arguments: used only when both are given, as in the reference."""
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200._native import SsfError
+    g = np.load(os.path.join(golden_dir, "tflow_afterpc_n2048.npz"))
+    net = TFlow(input_channels=4)
+    net.load_state_dict(tp.random_init_state_dict(int(g["weight_seed"]), 3, input_channels=4), strict=True)
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0).cuda()
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0).cuda()
+    f1 = torch.cat([pc1, torch.from_numpy(g["lab1"])[None, None].cuda()], dim=1)
+    f2 = torch.cat([pc2, torch.from_numpy(g["lab2"])[None, None].cuda()], dim=1)
+    flows, fps = net(pc1, pc2, f1, f2)
+    for i in range(3):
+        assert np.array_equal(fps[i][0].cpu().numpy(), g["fps%d" % (i + 1)])
+    errs = [float(np.abs(flows[i][0].cpu().numpy() - g["flow%d" % i]).max()) for i in range(4)]
+    print("4-channel input variant, flow max-abs error per level:", errs)
+    assert max(errs) <= FLOW_TOL
+    with pytest.raises(SsfError):
+        net(pc1, pc2)                      # Conv1d(4, 32) on 3-channel coordinates fails in the reference too
+    base = TFlow()
+    base.load_state_dict(tp.random_init_state_dict(0), strict=True)
+    a, _ = base(pc1, pc2)
+    b, _ = base(pc1, pc2, pc1, None)       # one of the two missing -> coordinates are used
+    c, _ = base(pc1, pc2, pc1, pc2)        # both given and equal to the coordinates -> same result
+    assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0])

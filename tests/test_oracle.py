@@ -123,3 +123,18 @@ def test_gmm_spec_matches_sklearn_golden_and_live(golden_dir):
     spec, labels, gm = gmm.check_against_sklearn(g["gt0_points"], g["gt0_flow"])
     assert np.array_equal(labels, spec["labels"]) and gm.n_iter_ == spec["n_iter"]
     assert np.array_equal(gmm.reference_bg_index(labels), spec["bg_index"])
+
+
+def test_tflow_port_afterpc_variant_matches_reference_golden(golden_dir, oracle_c):
+    """4-channel INPUT variant (TFlowV3_Occlussion_addSeg_afterPC.py:68); golden written by that unmodified file."""
+    g = np.load(os.path.join(golden_dir, "tflow_afterpc_n2048.npz"))
+    sd = tflow_port.random_init_state_dict(int(g["weight_seed"]), 3, input_channels=4)
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0)
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0)
+    f1 = torch.cat([pc1, torch.from_numpy(g["lab1"])[None, None]], dim=1)
+    f2 = torch.cat([pc2, torch.from_numpy(g["lab2"])[None, None]], dim=1)
+    flows, fps = tflow_port.tflow_forward(sd, pc1, pc2, feats1=f1, feats2=f2)
+    for i in range(3):
+        assert np.array_equal(fps[i][0].numpy(), g["fps%d" % (i + 1)])
+    for i in range(4):
+        assert np.abs(flows[i][0].numpy() - g["flow%d" % i]).max() <= 2e-5

@@ -8,7 +8,9 @@
 //         points (lane = point, one coalesced 512-byte load) are sorted across the lanes by a bitonic network and become
 //         the candidate list (lane j = j-th best); a few more nearest-first visits tighten the k-th distance, then every
 //         remaining block whose bound does not exceed it is visited in index order (re-tested as the bound shrinks).
-//         Survivors of a visited block are merged into the lane-distributed list with ballot / shuffle-up inserts.
+//         Survivors of a visited block are merged into the lane-distributed list with ballot / shuffle-up inserts; when a
+//         block has many of them (the first blocks of a query) the block is sorted across the lanes instead and merged with
+//         the list by one bitonic merge (min of the list and the reversed block = the 32 smallest keys).
 // Exactness: every box bound is computed with the SAME rounded operations as the point distance and each of them
 // (fsub, fmul, fadd) is monotone, so bound <= distance of every point inside the box holds in floating point, not
 // just in exact arithmetic; blocks are skipped only on bound > kth (strict), so index ties are never lost.
@@ -144,6 +146,8 @@ template <int NBL>
 __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
                                                                 const float* __restrict__ ws, int Nq, int npad, int nblk,
                                                                 float* __restrict__ dist, int* __restrict__ idx) {
+    // survivors of a block from which the sort-merge beats one-by-one insertion (measured: 6 for <= 64 blocks, 10-16 above)
+    constexpr int merge_min = NBL == 2 ? 6 : 12;
     extern __shared__ __align__(16) float4 sbox[];   // [nblk] lo | [nblk] hi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -184,21 +188,50 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
         auto pack = [](float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; };
         // evaluates block `blk` (lane = point) and merges the survivors into the lane-distributed sorted list
         KSTAT(0, 1);
+        // ascending bitonic sort of one key per lane
+        auto sort32 = [&](unsigned long long key) -> unsigned long long {
+#pragma unroll
+            for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                    if (take_min == (ok < key)) key = ok;
+                }
+            }
+            return key;
+        };
         auto visit = [&](int blk) {
             KSTAT(1, 1);
             const float4 p = __ldg(P + (size_t)blk * 32 + lane);
-            const unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+            unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
             unsigned mask = __ballot_sync(0xffffffffu, key < kth);
-            while (mask) {
-                const int src = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
-                if (ck >= kth) continue;   // warp-uniform: the k-th key tightened meanwhile
-                KSTAT(2, 1);
-                const int pos = __popc(__ballot_sync(0xffffffffu, list_k < ck));
-                const unsigned long long uk = __shfl_up_sync(0xffffffffu, list_k, 1);
-                list_k = lane == pos ? ck : (lane > pos ? uk : list_k);
+            if (__popc(mask) >= merge_min) {
+                // many survivors (the first blocks of a query): sort the block and merge it with the list in one go -- the
+                // element-wise min of the list and the reversed block is a bitonic sequence holding the 32 smallest keys
+                key = sort32(key);
+                const unsigned long long rev = __shfl_sync(0xffffffffu, key, 31 - lane);
+                unsigned long long m = rev < list_k ? rev : list_k;
+#pragma unroll
+                for (int j = 16; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, m, j);
+                    if (((lane & j) == 0) == (ok < m)) m = ok;
+                }
+                list_k = m;
                 kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+                KSTAT(2, 8);
+            } else {
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
+                    if (ck >= kth) continue;   // warp-uniform: the k-th key tightened meanwhile
+                    KSTAT(2, 1);
+                    const int pos = __popc(__ballot_sync(0xffffffffu, list_k < ck));
+                    const unsigned long long uk = __shfl_up_sync(0xffffffffu, list_k, 1);
+                    list_k = lane == pos ? ck : (lane > pos ? uk : list_k);
+                    kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+                }
             }
             kth_d = __uint_as_float((unsigned)(kth >> 32));
         };
@@ -234,17 +267,7 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
             float best;
             const int blk = pop_nearest(best);   // >= 0: there is at least one block
             const float4 p = __ldg(P + (size_t)blk * 32 + lane);
-            unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
-#pragma unroll
-            for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-                for (int j = kk >> 1; j > 0; j >>= 1) {
-                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
-                    const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
-                    if (take_min == (ok < key)) key = ok;
-                }
-            }
-            list_k = key;
+            list_k = sort32(pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)));
             kth = __shfl_sync(0xffffffffu, list_k, k - 1);
             kth_d = __uint_as_float((unsigned)(kth >> 32));
         }

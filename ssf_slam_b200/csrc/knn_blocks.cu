@@ -245,16 +245,11 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
                     best = lb[s];
                     bs = s;
                 }
-            int bblk = bs * 32 + lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, bblk, o);
-                if (ob < best || (ob == best && ok < bblk)) {
-                    best = ob;
-                    bblk = ok;
-                }
-            }
+            // warp-wide minimum by two integer reductions (bounds are non-negative floats: their bit patterns order like the
+            // values): the smallest bound, then the lowest block index among the lanes that hold it
+            const unsigned mn = __reduce_min_sync(0xffffffffu, __float_as_uint(best));
+            const int bblk = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(best) == mn ? (unsigned)(bs * 32 + lane) : 0x7fffffffu);
+            best = __uint_as_float(mn);
             best_out = best;
             if (best == CUDART_INF_F) return -1;
 #pragma unroll

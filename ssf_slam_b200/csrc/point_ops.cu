@@ -550,13 +550,14 @@ group_staged_kernel(const float* __restrict__ feat, const int* __restrict__ idx,
     }
 }
 
-__global__ void __launch_bounds__(STAGE_T)
+template <int GC, int T>
+__global__ void __launch_bounds__(T)
 three_interpolate_staged_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const float* __restrict__ w, int C,
-                                int M, int N, int chunk, float* __restrict__ out) {
-    extern __shared__ __align__(128) float srow[];   // [STAGE_GC][M]
+                                int M, int N, int chunk, int vec4, float* __restrict__ out) {
+    extern __shared__ __align__(128) float srow[];   // [GC][M]
     __shared__ __align__(8) uint64_t bar;
-    const int b = blockIdx.z, c0 = blockIdx.y * STAGE_GC;
-    const int nc = min(STAGE_GC, C - c0);
+    const int b = blockIdx.z, c0 = blockIdx.y * GC;
+    const int nc = min(GC, C - c0);
     if (threadIdx.x == 0) {
         ssf_mbar_init(&bar, 1);
         ssf_mbar_fence_init();
@@ -566,13 +567,35 @@ three_interpolate_staged_kernel(const float* __restrict__ feat, const int* __res
     __syncthreads();
     ssf_mbar_wait(&bar, 0);
     const int n_end = min(N, (int)(blockIdx.x + 1) * chunk);
-    for (int n = blockIdx.x * chunk + threadIdx.x; n < n_end; n += STAGE_T) {
+    if (vec4) {
+        // four consecutive query points per thread: their 12 indices and 12 weights are three 16-byte loads each, the four
+        // results of a channel leave as one streaming 16-byte store
+        const int4* ip4 = reinterpret_cast<const int4*>(idx + (size_t)b * N * 3);
+        const float4* wp4 = reinterpret_cast<const float4*>(w + (size_t)b * N * 3);
+        for (int n4 = (blockIdx.x * chunk) / 4 + threadIdx.x; n4 * 4 < n_end; n4 += T) {
+            const int4 ia = __ldg(ip4 + 3 * n4), ib = __ldg(ip4 + 3 * n4 + 1), ic = __ldg(ip4 + 3 * n4 + 2);
+            const float4 wa = __ldg(wp4 + 3 * n4), wb = __ldg(wp4 + 3 * n4 + 1), wc = __ldg(wp4 + 3 * n4 + 2);
+#pragma unroll
+            for (int c = 0; c < GC; ++c)
+                if (c < nc) {
+                    const float* r = srow + (size_t)c * M;
+                    float4 o;
+                    o.x = __fadd_rn(__fadd_rn(__fmul_rn(r[ia.x], wa.x), __fmul_rn(r[ia.y], wa.y)), __fmul_rn(r[ia.z], wa.z));
+                    o.y = __fadd_rn(__fadd_rn(__fmul_rn(r[ia.w], wa.w), __fmul_rn(r[ib.x], wb.x)), __fmul_rn(r[ib.y], wb.y));
+                    o.z = __fadd_rn(__fadd_rn(__fmul_rn(r[ib.z], wb.z), __fmul_rn(r[ib.w], wb.w)), __fmul_rn(r[ic.x], wc.x));
+                    o.w = __fadd_rn(__fadd_rn(__fmul_rn(r[ic.y], wc.y), __fmul_rn(r[ic.z], wc.z)), __fmul_rn(r[ic.w], wc.w));
+                    __stcs(reinterpret_cast<float4*>(out + ((size_t)b * C + c0 + c) * N) + n4, o);
+                }
+        }
+        return;
+    }
+    for (int n = blockIdx.x * chunk + threadIdx.x; n < n_end; n += T) {
         const int* ip = idx + ((size_t)b * N + n) * 3;
         const float* wp = w + ((size_t)b * N + n) * 3;
         const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
         const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
 #pragma unroll
-        for (int c = 0; c < STAGE_GC; ++c)
+        for (int c = 0; c < GC; ++c)
             if (c < nc) {
                 const float* r = srow + (size_t)c * M;
                 __stcs(out + ((size_t)b * C + c0 + c) * N + n,
@@ -652,17 +675,24 @@ extern "C" int ssf_three_interpolate(const float* feat, const int* idx, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || C <= 0 || N <= 0) return ssf_arg_error("three_interpolate: empty input");
     if (can_stage(feat, M) && N >= M) {
-        const size_t smem = (size_t)M * 4 * STAGE_GC;
+        // every CTA re-reads the 24 N bytes of indices and weights of its points, so it stages three channels when two such
+        // CTAs still share an SM (one CTA per SM with 4-6 rows measured slower: its load phase is not overlapped)
+        const int gc = (size_t)M * 4 * 3 <= 100 * 1024 ? 3 : 2;
+        const size_t smem = (size_t)M * 4 * gc;
         int chunk = N;
         while (chunk / 2 >= M && chunk % 2 == 0) chunk /= 2;
-        static size_t attr = 0;
-        if (smem > attr) {
-            cudaError_t e = cudaFuncSetAttribute(three_interpolate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(three_interpolate_staged_kernel<2, STAGE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(three_interpolate_staged_kernel<3, STAGE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return ssf_set_error(e);
-            attr = 200 * 1024;
+            attr = true;
         }
-        dim3 grid((N + chunk - 1) / chunk, (C + STAGE_GC - 1) / STAGE_GC, B);
-        three_interpolate_staged_kernel<<<grid, STAGE_T, smem, st>>>(feat, idx, weight, C, M, N, chunk, out);
+        dim3 grid((N + chunk - 1) / chunk, (C + gc - 1) / gc, B);
+        const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        const int vec4 = (N % 4 == 0 && chunk % 4 == 0 && al16(idx) && al16(weight) && al16(out)) ? 1 : 0;
+        if (gc == 3) three_interpolate_staged_kernel<3, STAGE_T><<<grid, STAGE_T, smem, st>>>(feat, idx, weight, C, M, N, chunk, vec4, out);
+        else three_interpolate_staged_kernel<2, STAGE_T><<<grid, STAGE_T, smem, st>>>(feat, idx, weight, C, M, N, chunk, vec4, out);
         ssf_count_launch();
         SSF_LAUNCH_CHECK();
         return SSF_OK;

@@ -113,11 +113,13 @@ def test_grouping_and_gather(pu, C, N, M, S):
     assert np.array_equal(g1, po.gather_operation(torch.from_numpy(feat), torch.from_numpy(idx[:, :, 0].copy())).numpy())
 
 
-def test_three_interpolate(pu):
+@pytest.mark.parametrize("C,M,N", [(33, 500, 1000), (6, 8192, 8192), (5, 500, 1002), (3, 64, 40), (4, 2048, 8192)])
+def test_three_interpolate(pu, C, M, N):
+    """staged + four-points-per-thread path (N % 4 == 0), staged scalar path, plain path (N < M)"""
     rng = np.random.default_rng(9)
-    feat = rng.standard_normal((2, 33, 500)).astype(np.float32)
-    idx = rng.integers(0, 500, (2, 1000, 3)).astype(np.int32)
-    w = rng.random((2, 1000, 3)).astype(np.float32)
+    feat = rng.standard_normal((2, C, M)).astype(np.float32)
+    idx = rng.integers(0, M, (2, N, 3)).astype(np.int32)
+    w = rng.random((2, N, 3)).astype(np.float32)
     got = pu.three_interpolate(_cuda(feat), _cuda(idx), _cuda(w)).cpu().numpy()
     want = po.three_interpolate(torch.from_numpy(feat), torch.from_numpy(idx), torch.from_numpy(w)).numpy()
     assert np.array_equal(got, want)

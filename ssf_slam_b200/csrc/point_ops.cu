@@ -462,11 +462,69 @@ ball_query_kernel(float r2, int nsample, const float* __restrict__ xyz, const fl
     }
 }
 
+// Few query points (B * S below one thread per lane of the machine, e.g. BASELINE config 4: 2048 centres in 65536 points):
+// one warp per BQ_Q queries, lane = reference point.  A step tests 32 consecutive points; the ballot of the hits is already in
+// index order, so a hit's output slot is the running count plus the number of hits in lower lanes.  Same result as the
+// thread-per-query kernel (first nsample hits in ascending index, padded with the first hit, total count).
+constexpr int BQ_Q = 2;
+
+__global__ void __launch_bounds__(256)
+ball_query_warp_kernel(float r2, int nsample, const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S,
+                       int* __restrict__ idx, int* __restrict__ cnt) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = ((int)blockIdx.x * 8 + warp) * BQ_Q;
+    if (s0 >= S) return;
+    float qx[BQ_Q], qy[BQ_Q], qz[BQ_Q];
+    int c[BQ_Q], first[BQ_Q];
+#pragma unroll
+    for (int q = 0; q < BQ_Q; ++q) {
+        const float* cp = new_xyz + ((size_t)b * S + min(s0 + q, S - 1)) * 3;
+        qx[q] = __ldg(cp); qy[q] = __ldg(cp + 1); qz[q] = __ldg(cp + 2);
+        c[q] = 0;
+        first[q] = 0;
+    }
+    const float* P = xyz + (size_t)b * N * 3;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < N; base += 32) {
+        const int r = base + lane;
+        const bool in = r < N;
+        const int rc = in ? r : N - 1;
+        const float x = __ldg(P + 3 * rc), y = __ldg(P + 3 * rc + 1), z = __ldg(P + 3 * rc + 2);
+        bool done = cnt == nullptr;
+#pragma unroll
+        for (int q = 0; q < BQ_Q; ++q) {
+            const bool hit = in && ssf_sqdist(qx[q], qy[q], qz[q], x, y, z) <= r2;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                if (c[q] == 0) first[q] = base + __ffs(m) - 1;
+                const int pos = c[q] + __popc(m & lt);
+                if (hit && pos < nsample && s0 + q < S) idx[((size_t)b * S + s0 + q) * nsample + pos] = r;
+                c[q] += __popc(m);
+            }
+            done = done && c[q] >= nsample;
+        }
+        if (done) break;   // counts not asked for: stop once every query of the warp has its nsample hits
+    }
+#pragma unroll
+    for (int q = 0; q < BQ_Q; ++q) {
+        if (s0 + q >= S) continue;
+        for (int j = min(c[q], nsample) + lane; j < nsample; j += 32) idx[((size_t)b * S + s0 + q) * nsample + j] = first[q];
+        if (cnt != nullptr && lane == 0) cnt[(size_t)b * S + s0 + q] = c[q];
+    }
+}
+
 extern "C" int ssf_ball_query(float radius, int nsample, const float* xyz, const float* new_xyz, int B, int N, int S,
                               int* idx, int* cnt, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || S <= 0 || N <= 0 || nsample <= 0) return ssf_arg_error("ball_query: empty input");
     const float r2 = radius * radius;  // fp32 product, as the spec
+    if ((long long)B * S <= 32768) {   // too few queries to fill the machine with one thread each
+        dim3 wgrid((S + 8 * BQ_Q - 1) / (8 * BQ_Q), B);
+        ball_query_warp_kernel<<<wgrid, 256, 0, st>>>(r2, nsample, xyz, new_xyz, N, S, idx, cnt);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
     dim3 grid((S + SCAN_T - 1) / SCAN_T, B);
     ball_query_kernel<<<grid, SCAN_T, 0, st>>>(r2, nsample, xyz, new_xyz, N, S, idx, cnt);
     ssf_count_launch();

@@ -87,7 +87,7 @@ def ball_query(radius, nsample, xyz, new_xyz, return_count=False):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     idx = torch.empty(B, S, nsample, dtype=torch.int32, device=xyz.device)
-    cnt = torch.empty(B, S, dtype=torch.int32, device=xyz.device)
+    cnt = torch.empty(B, S, dtype=torch.int32, device=xyz.device) if return_count else None   # without counts a query stops at nsample hits
     nat.check(nat.lib().ssf_ball_query(float(radius), int(nsample), nat.ptr(xyz), nat.ptr(new_xyz), B, N, S, nat.ptr(idx),
                                        nat.ptr(cnt), nat.stream()))
     return (idx, cnt) if return_count else idx

@@ -100,6 +100,17 @@ def test_ball_query(pu, N, S, radius, nsample):
     oi, oc = po.c_ball_query(radius, nsample, xyz, new)
     assert np.array_equal(bc.cpu().numpy(), oc)
     assert np.array_equal(bi.cpu().numpy(), oi)
+    assert np.array_equal(pu.ball_query(radius, nsample, _cuda(xyz), _cuda(new)).cpu().numpy(), oi)   # no counts: early exit
+
+
+def test_ball_query_many_queries_thread_per_query_kernel(pu):
+    """B * S above the warp-per-query threshold (32768): the thread-per-query kernel; and just below it: the warp kernel."""
+    for B, S in ((20, 2048), (16, 2048)):
+        xyz = _cloud(77, B, 1024, scale=10.0)
+        new = np.concatenate([xyz, xyz[:, ::-1] + 0.3], axis=1).copy()[:, :S]
+        bi, bc = pu.ball_query(1.5, 16, _cuda(xyz), _cuda(new), return_count=True)
+        oi, oc = po.c_ball_query(1.5, 16, xyz, new)
+        assert np.array_equal(bc.cpu().numpy(), oc) and np.array_equal(bi.cpu().numpy(), oi)
 
 
 @pytest.mark.parametrize("C,N,M,S", [(3, 8192, 2048, 16), (96, 8192, 8192, 16), (64, 2048, 8192, 7), (5, 100, 33, 3), (1, 7, 1, 1)])

@@ -369,20 +369,32 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                                 for (int j = 0; j < 8; ++j) v[q][j] += h[j];
                             }
                         }
+                        // bias + direction term on packed fp32x2 FMAs (two channels per instruction), then the activation
+                        const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             float bb[8];
                             lds8(sB1 + k0 + q * 8, bb);
+                            float2 acc[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[j] = __fadd2_rn(make_float2(v[q][2 * j], v[q][2 * j + 1]), make_float2(bb[2 * j], bb[2 * j + 1]));
                             if (need_dir) {
                                 float w0[8], w1[8], w2[8];
                                 lds8(sWd1 + k0 + q * 8, w0);
                                 lds8(sWd1 + a.K + k0 + q * 8, w1);
                                 lds8(sWd1 + 2 * a.K + k0 + q * 8, w2);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[q][j] += dx * w0[j] + dy * w1[j] + dz * w2[j];
+                                for (int j = 0; j < 4; ++j) {
+                                    acc[j] = __ffma2_rn(dx2, make_float2(w0[2 * j], w0[2 * j + 1]), acc[j]);
+                                    acc[j] = __ffma2_rn(dy2, make_float2(w1[2 * j], w1[2 * j + 1]), acc[j]);
+                                    acc[j] = __ffma2_rn(dz2, make_float2(w2[2 * j], w2[2 * j + 1]), acc[j]);
+                                }
                             }
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[q][j] = act_apply(v[q][j] + bb[j], a.act1);
+                            for (int j = 0; j < 4; ++j) {
+                                v[q][2 * j] = act_apply(acc[j].x, a.act1);
+                                v[q][2 * j + 1] = act_apply(acc[j].y, a.act1);
+                            }
                         }
                     }
                     // each warpgroup owns SPW of the A stages and waits on them strictly in order (an mbarrier

@@ -53,35 +53,12 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ o
         const float lx = s_xyz[3 * last], ly = s_xyz[3 * last + 1], lz = s_xyz[3 * last + 2];
         float best = -1.f;
         unsigned besti = 0xffffffffu;
-        // two points per packed fp32x2 instruction (add / mul only, each lane rounded like the scalar operation: the distance
-        // stays ((dx*dx)+(dy*dy))+(dz*dz) without FMA; p - l is computed as p + (-l), the same IEEE result)
-        const float2 nlx = make_float2(-lx, -lx), nly = make_float2(-ly, -ly), nlz = make_float2(-lz, -lz);
 #pragma unroll
-        for (int j = 0; j + 1 < PPT; j += 2) {
-            const float2 dx = __fadd2_rn(make_float2(px[j], px[j + 1]), nlx);
-            const float2 dy = __fadd2_rn(make_float2(py[j], py[j + 1]), nly);
-            const float2 dz = __fadd2_rn(make_float2(pz[j], pz[j + 1]), nlz);
-            const float2 d2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
-            const float dd[2] = {d2.x, d2.y};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int i = tid + (j + u) * T;
-                if (i < N) {
-                    const float m = fminf(md[j + u], dd[u]);
-                    md[j + u] = m;
-                    if (m > best) {
-                        best = m;
-                        besti = (unsigned)i;
-                    }
-                }
-            }
-        }
-        if (PPT & 1) {
-            constexpr int j = PPT - 1;
-            const int i = tid + j * T;
+        for (int j = 0; j < PPT; ++j) {
+            int i = tid + j * T;
             if (i < N) {
-                const float d = ssf_sqdist(px[j], py[j], pz[j], lx, ly, lz);
-                const float m = fminf(md[j], d);
+                float d = ssf_sqdist(px[j], py[j], pz[j], lx, ly, lz);
+                float m = fminf(md[j], d);
                 md[j] = m;
                 if (m > best) {
                     best = m;

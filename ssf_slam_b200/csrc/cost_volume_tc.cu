@@ -74,6 +74,13 @@ __device__ __forceinline__ void split_store32(const float (&v)[32], uint32_t t_h
     }
 }
 __device__ __forceinline__ float leaky(float v) { return fmaxf(v, 0.1f * v); }
+// LeakyReLU(0.1) of (a + b) for two channels: packed fp32x2 add and multiply, scalar max
+__device__ __forceinline__ void leaky_add2(float& a0, float& a1, float b0, float b1) {
+    const float2 x = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
+    const float2 y = __fmul2_rn(x, make_float2(0.1f, 0.1f));
+    a0 = fmaxf(x.x, y.x);
+    a1 = fmaxf(x.y, y.y);
+}
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
     float a[16], b[16];
@@ -312,10 +319,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
                     const float4 bb = lds4(b2 + q4 * 4);
-                    v[q4 * 4] = leaky(v[q4 * 4] + bb.x);
-                    v[q4 * 4 + 1] = leaky(v[q4 * 4 + 1] + bb.y);
-                    v[q4 * 4 + 2] = leaky(v[q4 * 4 + 2] + bb.z);
-                    v[q4 * 4 + 3] = leaky(v[q4 * 4 + 3] + bb.w);
+                    leaky_add2(v[q4 * 4], v[q4 * 4 + 1], bb.x, bb.y);
+                    leaky_add2(v[q4 * 4 + 2], v[q4 * 4 + 3], bb.z, bb.w);
                     *reinterpret_cast<float4*>(sOwn + r * LDA + c0 + q4 * 4) = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
                 }
                 split_store32(v, t_hi, t_lo);
@@ -476,6 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
                 const float* h3 = sH3 + p * CM + c0;
                 const float* wd = sPar + P_W3D + c0;
                 const float dx = psx - pqx, dy = psy - pqy, dz = psz - pqz;
+                const float2 dx2 = make_float2(dx, dx), dy2 = make_float2(dy, dy), dz2 = make_float2(dz, dz);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     float t[16];
@@ -486,10 +492,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
                         const int cq = hh * 4 + q4;
                         const float4 h = lds4(h3 + cq * 4);
                         const float4 w0 = lds4(wd + cq * 4), w1 = lds4(wd + CM + cq * 4), w2 = lds4(wd + 2 * CM + cq * 4);
-                        t[q4 * 4] = leaky(t[q4 * 4] + h.x + (dx * w0.x + dy * w1.x + dz * w2.x));
-                        t[q4 * 4 + 1] = leaky(t[q4 * 4 + 1] + h.y + (dx * w0.y + dy * w1.y + dz * w2.y));
-                        t[q4 * 4 + 2] = leaky(t[q4 * 4 + 2] + h.z + (dx * w0.z + dy * w1.z + dz * w2.z));
-                        t[q4 * 4 + 3] = leaky(t[q4 * 4 + 3] + h.w + (dx * w0.w + dy * w1.w + dz * w2.w));
+                        // D + H3[n] + W3d . dir on packed fp32x2 FMAs (two channels per instruction), then LeakyReLU
+                        float2 a01 = __fadd2_rn(make_float2(t[q4 * 4], t[q4 * 4 + 1]), make_float2(h.x, h.y));
+                        float2 a23 = __fadd2_rn(make_float2(t[q4 * 4 + 2], t[q4 * 4 + 3]), make_float2(h.z, h.w));
+                        a01 = __ffma2_rn(dx2, make_float2(w0.x, w0.y), a01);
+                        a23 = __ffma2_rn(dx2, make_float2(w0.z, w0.w), a23);
+                        a01 = __ffma2_rn(dy2, make_float2(w1.x, w1.y), a01);
+                        a23 = __ffma2_rn(dy2, make_float2(w1.z, w1.w), a23);
+                        a01 = __ffma2_rn(dz2, make_float2(w2.x, w2.y), a01);
+                        a23 = __ffma2_rn(dz2, make_float2(w2.z, w2.w), a23);
+                        const float2 s01 = __fmul2_rn(a01, make_float2(0.1f, 0.1f)), s23 = __fmul2_rn(a23, make_float2(0.1f, 0.1f));
+                        t[q4 * 4] = fmaxf(a01.x, s01.x);
+                        t[q4 * 4 + 1] = fmaxf(a01.y, s01.y);
+                        t[q4 * 4 + 2] = fmaxf(a23.x, s23.x);
+                        t[q4 * 4 + 3] = fmaxf(a23.y, s23.y);
                     }
 #pragma unroll
                     for (int c8 = 0; c8 < 2; ++c8) {
@@ -548,10 +564,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
                     const float4 bb = lds4(bn + q4 * 4);
-                    v[q4 * 4] = fmaxf(v[q4 * 4] + bb.x, 0.f);
-                    v[q4 * 4 + 1] = fmaxf(v[q4 * 4 + 1] + bb.y, 0.f);
-                    v[q4 * 4 + 2] = fmaxf(v[q4 * 4 + 2] + bb.z, 0.f);
-                    v[q4 * 4 + 3] = fmaxf(v[q4 * 4 + 3] + bb.w, 0.f);
+                    const float2 r01 = __fadd2_rn(make_float2(v[q4 * 4], v[q4 * 4 + 1]), make_float2(bb.x, bb.y));
+                    const float2 r23 = __fadd2_rn(make_float2(v[q4 * 4 + 2], v[q4 * 4 + 3]), make_float2(bb.z, bb.w));
+                    v[q4 * 4] = fmaxf(r01.x, 0.f);
+                    v[q4 * 4 + 1] = fmaxf(r01.y, 0.f);
+                    v[q4 * 4 + 2] = fmaxf(r23.x, 0.f);
+                    v[q4 * 4 + 3] = fmaxf(r23.y, 0.f);
                 }
                 split_store32(v, t_hi, t_lo);
                 tc_st_wait();

@@ -52,7 +52,6 @@ struct DenseCfg {
     int resident;    // whole image resident (nk <= nstage)
     int nd;          // accumulator buffers
     int n_tiles;     // row tiles
-    int wsplit;      // bulk copies per streamed weight chunk
     int pd;          // A chunks a producer warp keeps in flight ahead of the one it converts (ring of pd + 1 staging tiles)
 };
 
@@ -187,9 +186,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 const int st = g % cfg.nstage;
                 if (g >= cfg.nstage) ssf_mbar_wait(&w_empty[st], (uint32_t)((g / cfg.nstage - 1) & 1));
                 ssf_mbar_expect_tx(&w_full[st], wchunk);
-                const uint32_t part = wchunk / (uint32_t)cfg.wsplit;
-                for (int pp = 0; pp < cfg.wsplit; ++pp)
-                    ssf_bulk_g2s(sW + (size_t)st * wchunk + pp * part, wsrc + (size_t)(g % nk) * wchunk + pp * part, part, &w_full[st]);
+                ssf_bulk_g2s(sW + (size_t)st * wchunk, wsrc + (size_t)(g % nk) * wchunk, wchunk, &w_full[st]);
             }
         }
     };
@@ -623,7 +620,6 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     cfg.nstage = cfg.resident ? cfg.nk : (int)(W_SMEM_MAX / wchunk);
     if (cfg.nstage > 16) cfg.nstage = 16;
     cfg.n_tiles = (int)((a.rows + 127) / 128);
-    { const char* e = getenv("SSF_W_SPLIT"); cfg.wsplit = e ? atoi(e) : 1; if (cfg.wsplit < 1 || cfg.wsplit > 16) cfg.wsplit = 1; }
     const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
     const size_t tile_b = (size_t)32 * STG_LD * 4;   // one staging tile of a warp
     const int light_mode = dense_variant();
@@ -650,11 +646,9 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));
     // shared-memory plan: staging tiles (producer rings with 1 or 2 chunks in flight + the STORE epilogue tiles), then the
     // weight image: resident when it fits in what is left (at most W_SMEM_MAX), else a ring of whole chunks
-    static int full_mode = -1;
-    if (full_mode < 0) { const char* e = getenv("SSF_DENSE_FULL"); full_mode = e ? atoi(e) : 1; }
     const size_t smem_full = smem_fixed + (size_t)(8 * 2 + 8) * tile_b;
     // (measured: the SA / SU pooling layers gain 4-8 %; layers that also add a per-point block H lose under the 96-register cap)
-    const bool full = light_mode && full_mode && !light && !wide && a.a_mode == 1 && a.H == nullptr && a.epi_mode != SSF_EPI_DOT && cfg.Nt >= 64 &&
+    const bool full = light_mode && !light && !wide && a.a_mode == 1 && a.H == nullptr && a.epi_mode != SSF_EPI_DOT && cfg.Nt >= 64 &&
                       cfg.Nt <= 128 && cfg.resident && smem_full <= (size_t)227 * 1024;
     const int n_pw = (light || wide) ? 4 : 8, n_ew = (wide || full) ? 8 : 4;
     const size_t smem_cap = light ? (size_t)LIGHT_SMEM_MAX : (size_t)227 * 1024;

@@ -631,7 +631,11 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     // 256-column tiles (single accumulator): two epilogue warpgroups (the DOT epilogue needs whole rows in one thread)
     // ... and for plain-row layers of >= 64 columns, whose single producer warpgroup keeps up (measured: 8-25 % faster; the
     // grouped first layer needs both producer warpgroups)
-    const bool wide = light_mode && !light && a.epi_mode != SSF_EPI_DOT && (cfg.Nt == 256 || (a.a_mode == 0 && cfg.Nt >= 64));
+    const size_t smem_full = smem_fixed + (size_t)(8 * 2 + 8) * tile_b;
+    const bool full_ok = cfg.Nt >= 64 && cfg.Nt <= 128 && cfg.resident && smem_full <= (size_t)227 * 1024 && a.epi_mode != SSF_EPI_DOT;
+    // plain-row layers of 64 columns with a small weight image: 2 + 2 warpgroups (measured 12-19 % faster than 1 + 2; no gain at 128)
+    const bool full_r = light_mode && !light && a.a_mode == 0 && cfg.Nt == 64 && full_ok;
+    const bool wide = light_mode && !light && !full_r && a.epi_mode != SSF_EPI_DOT && (cfg.Nt == 256 || (a.a_mode == 0 && cfg.Nt >= 64));
     cfg.nd = light ? 2 : ((2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1);
     static bool attr_set = false;
     if (!attr_set) {
@@ -646,10 +650,8 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));
     // shared-memory plan: staging tiles (producer rings with 1 or 2 chunks in flight + the STORE epilogue tiles), then the
     // weight image: resident when it fits in what is left (at most W_SMEM_MAX), else a ring of whole chunks
-    const size_t smem_full = smem_fixed + (size_t)(8 * 2 + 8) * tile_b;
     // (measured: the SA / SU pooling layers gain 4-8 %; layers that also add a per-point block H lose under the 96-register cap)
-    const bool full = light_mode && !light && !wide && a.a_mode == 1 && a.H == nullptr && a.epi_mode != SSF_EPI_DOT && cfg.Nt >= 64 &&
-                      cfg.Nt <= 128 && cfg.resident && smem_full <= (size_t)227 * 1024;
+    const bool full = full_r || (light_mode && !light && !wide && a.a_mode == 1 && a.H == nullptr && full_ok);
     const int n_pw = (light || wide) ? 4 : 8, n_ew = (wide || full) ? 8 : 4;
     const size_t smem_cap = light ? (size_t)LIGHT_SMEM_MAX : (size_t)227 * 1024;
     const size_t smem_par = (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;

@@ -177,11 +177,13 @@ def test_dense_tc_light_variant_is_bit_identical(rows, K, N, grouped, epi):
     prev = F_.set_dense_variant(2)
     try:
         y_light = run()
+        F_.set_dense_variant(1)      # the default policy (wide / full / light chosen per layer)
+        y_default = run()
         F_.set_dense_variant(0)
         y_heavy = run()
     finally:
         F_.set_dense_variant(prev)
-    assert torch.equal(y_light, y_heavy)
+    assert torch.equal(y_light, y_heavy) and torch.equal(y_default, y_heavy)
     if not grouped:
         ref = _act(X.cpu().double() @ W.double().t() + bias.double(), 2)
     else:   # MAX / DOT without a per-row epilogue term: bias and activation are applied after the pooling

@@ -53,6 +53,11 @@ int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, void* strea
 int ssf_knn_blocks_search(int k, const float* query, const float* query_add, const float* ws, int B, int Nq, int Nr,
                           float* dist, int* idx, void* stream);
 
+/* Same result by a brute-force scan with one warp per two queries (lane = reference point): for the few-queries / large-cloud
+ * corner (B * Nq <= 32768 and Nr > 16384, e.g. 2048 centres in 65536 points) where one thread per query leaves the GPU empty */
+int ssf_knn_warp_scan(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,
+                      float* dist, int* idx, void* stream);
+
 /* three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3], idx[B,n,3]); ASF/utils/soflow.py:1241,1459 */
 int ssf_three_nn(const float* query, const float* ref, int B, int Nq, int Nr, float* dist, int* idx, void* stream);
 

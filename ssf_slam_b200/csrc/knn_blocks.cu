@@ -302,6 +302,84 @@ __global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const flo
     }
 }
 
+// Brute-force scan, one warp per KS_Q queries (lane = reference point, 32 consecutive points per step), for reference clouds
+// too large for the block index when there are too few queries to fill the machine with one thread each (BASELINE config 4:
+// 2048 centres in 65536 points).  Same keys, same list operations and therefore the same result as every other kNN here.
+constexpr int KS_Q = 2;
+
+__global__ void __launch_bounds__(256) knn_warp_scan_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
+                                                            const float* __restrict__ ref, int Nq, int Nr,
+                                                            float* __restrict__ dist, int* __restrict__ idx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+    const int q0 = ((int)blockIdx.x * 8 + warp) * KS_Q;
+    if (q0 >= Nq) return;
+    auto pack = [](float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; };
+    float qx[KS_Q], qy[KS_Q], qz[KS_Q];
+    unsigned long long list_k[KS_Q], kth[KS_Q];
+#pragma unroll
+    for (int u = 0; u < KS_Q; ++u) {
+        const size_t qi = (size_t)b * Nq + min(q0 + u, Nq - 1);
+        qx[u] = __ldg(query + qi * 3); qy[u] = __ldg(query + qi * 3 + 1); qz[u] = __ldg(query + qi * 3 + 2);
+        if (qadd != nullptr) {
+            qx[u] = __fadd_rn(qx[u], __ldg(qadd + qi * 3));
+            qy[u] = __fadd_rn(qy[u], __ldg(qadd + qi * 3 + 1));
+            qz[u] = __fadd_rn(qz[u], __ldg(qadd + qi * 3 + 2));
+        }
+        list_k[u] = kth[u] = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+    }
+    const float* P = ref + (size_t)b * Nr * 3;
+    for (int base = 0; base < Nr; base += 32) {
+        const int r = base + lane;
+        const bool in = r < Nr;
+        const int rc = in ? r : Nr - 1;
+        const float x = __ldg(P + 3 * rc), y = __ldg(P + 3 * rc + 1), z = __ldg(P + 3 * rc + 2);
+#pragma unroll
+        for (int u = 0; u < KS_Q; ++u) {
+            unsigned long long key = in ? pack(ssf_sqdist(qx[u], qy[u], qz[u], x, y, z), r) : 0x7f8000007fffffffull;
+            unsigned mask = __ballot_sync(0xffffffffu, key < kth[u]);
+            if (__popc(mask) >= 12) {   // sort the 32 keys across the lanes and merge them with the list (see the block search)
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                        const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                        if (take_min == (ok < key)) key = ok;
+                    }
+                }
+                const unsigned long long rev = __shfl_sync(0xffffffffu, key, 31 - lane);
+                unsigned long long m = rev < list_k[u] ? rev : list_k[u];
+#pragma unroll
+                for (int j = 16; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, m, j);
+                    if (((lane & j) == 0) == (ok < m)) m = ok;
+                }
+                list_k[u] = m;
+                kth[u] = __shfl_sync(0xffffffffu, m, k - 1);
+            } else {
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
+                    if (ck >= kth[u]) continue;   // warp-uniform
+                    const int pos = __popc(__ballot_sync(0xffffffffu, list_k[u] < ck));
+                    const unsigned long long uk = __shfl_up_sync(0xffffffffu, list_k[u], 1);
+                    list_k[u] = lane == pos ? ck : (lane > pos ? uk : list_k[u]);
+                    kth[u] = __shfl_sync(0xffffffffu, list_k[u], k - 1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < KS_Q; ++u) {
+        if (q0 + u < Nq && lane < k) {
+            const size_t o = ((size_t)b * Nq + q0 + u) * k + lane;
+            idx[o] = (int)(unsigned)(list_k[u] & 0xffffffffull);
+            if (dist != nullptr) dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(list_k[u] >> 32)));
+        }
+    }
+}
+
 inline int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -357,6 +435,19 @@ extern "C" int ssf_knn_blocks_search(int k, const float* query, const float* que
         knn_blocks_search_kernel<8><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
     else
         knn_blocks_search_kernel<16><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+// brute force with one warp per two queries: any Nr, meant for few queries (B * Nq <= 32768) against a large cloud
+extern "C" int ssf_knn_warp_scan(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,
+                                 float* dist, int* idx, void* stream) {
+    if (B <= 0 || Nq <= 0) return ssf_arg_error("knn_warp_scan: empty input");
+    if (k <= 0 || k > 32) return ssf_arg_error("knn: k must be in [1,32]");
+    if (k > Nr) return ssf_arg_error("knn: k exceeds the number of reference points");
+    dim3 grid((Nq + 8 * KS_Q - 1) / (8 * KS_Q), B);
+    knn_warp_scan_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, query, query_add, ref, Nq, Nr, dist, idx);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

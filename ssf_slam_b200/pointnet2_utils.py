@@ -69,6 +69,11 @@ def knn(k, unknown, known, offset=None):
         nat.check(L.ssf_knn_blocks_search(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(ws), B, Nq, Nr, nat.ptr(dist),
                                           nat.ptr(idx), nat.stream()))
         return dist, idx
+    if Nr > 16384 and B * Nq <= 32768:
+        # few queries against a large cloud: one warp per two queries (one thread per query would leave the GPU empty)
+        nat.check(L.ssf_knn_warp_scan(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(known), B, Nq, Nr, nat.ptr(dist),
+                                      nat.ptr(idx), nat.stream()))
+        return dist, idx
     nat.check(L.ssf_knn_offset(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(known), B, Nq, Nr, nat.ptr(dist),
                                 nat.ptr(idx), nat.stream()))
     return dist, idx

@@ -202,3 +202,18 @@ def test_segment_softmax_sum_fused(B, L, C, n_seg, hot):
     assert float((got - want).abs().max()) < 1e-5
     again = F_.segment_softmax_sum(logit.cuda(), val.cuda().contiguous(), F_.build_csr(key.cuda(), n_seg), n_seg).cpu().double()
     assert torch.equal(got, again)   # deterministic
+
+
+@pytest.mark.parametrize("B,Nq,Nr,k", [(2, 300, 20000, 16), (1, 2048, 65536, 16), (2, 77, 17000, 5), (1, 33, 16385, 32)])
+def test_knn_warp_scan_large_cloud_few_queries(pu, B, Nq, Nr, k):
+    """Nr above the block-index limit with few queries: the warp-per-two-queries scan; same (distance, index) order as the oracle,
+    with exact duplicates in the cloud and queries on reference points."""
+    ref = _cloud(Nq + Nr, B, Nr)
+    q = _cloud(3 * Nq + 1, B, Nq, dup=False)
+    q[:, : Nq // 2] = ref[:, : Nq // 2]
+    d, i = pu.knn(k, _cuda(q), _cuda(ref))
+    od, oi = po.c_knn(k, q, ref)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+    off = (np.random.default_rng(4).standard_normal(q.shape) * 0.3).astype(np.float32)
+    _, i2 = pu.knn(k, _cuda(q), _cuda(ref), offset=_cuda(off))
+    assert np.array_equal(i2.cpu().numpy(), po.c_knn(k, q + off, ref)[1])

@@ -21,9 +21,6 @@ import time
 
 import numpy as np
 
-# keep NCCL's version banner off stdout (rank 0 prints exactly one JSON line); must be set before NCCL is loaded
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -235,7 +232,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; rank 0's stdout must carry exactly one JSON
+        # line, so file descriptor 1 points at stderr until the first collective has completed
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     nat.require_device()
     B, N, K, Wm = args.batch, args.npoints, args.steps, args.warmup
 

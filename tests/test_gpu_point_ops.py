@@ -217,3 +217,30 @@ def test_knn_warp_scan_large_cloud_few_queries(pu, B, Nq, Nr, k):
     off = (np.random.default_rng(4).standard_normal(q.shape) * 0.3).astype(np.float32)
     _, i2 = pu.knn(k, _cuda(q), _cuda(ref), offset=_cuda(off))
     assert np.array_equal(i2.cpu().numpy(), po.c_knn(k, q + off, ref)[1])
+
+
+def test_error_behaviour_python_exceptions(pu):
+    """Errors are Python exceptions (the reference's extension raises too; there are no status codes at the B-op boundary,
+    SURVEY 8(b)): empty inputs, CPU tensors (no CPU fallback), arguments out of range."""
+    from ssf_slam_b200._native import SsfError
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    zi = lambda *s: torch.zeros(*s, dtype=torch.int32, device="cuda")
+    with pytest.raises(SsfError):
+        pu.furthest_point_sample(z(1, 0, 3), 4)                       # empty cloud
+    with pytest.raises(SsfError):
+        pu.knn(3, z(1, 0, 3), z(1, 10, 3))                            # no queries
+    with pytest.raises(SsfError):
+        pu.knn(33, z(1, 4, 3), z(1, 100, 3))                          # k > 32
+    with pytest.raises(SsfError):
+        pu.ball_query(1.0, 0, z(1, 10, 3), z(1, 2, 3))                # nsample = 0
+    with pytest.raises(SsfError):
+        pu.grouping_operation(z(1, 0, 8), zi(1, 2, 2))                # no channels
+    with pytest.raises(SsfError):
+        pu.furthest_point_sample(torch.zeros(1, 16, 3), 4)            # CPU tensor: the product path has no CPU fallback
+    with pytest.raises(SsfError):
+        pu.knn(3, torch.zeros(1, 4, 3), torch.zeros(1, 10, 3))
+    # ragged / tiny but valid inputs still work
+    assert pu.furthest_point_sample(z(2, 1, 3), 1).tolist() == [[0], [0]]
+    d, i = pu.knn(1, z(1, 1, 3), z(1, 1, 3))
+    assert i.tolist() == [[[0]]] and float(d.abs().max()) == 0.0
+    assert pu.ball_query(1.0, 3, z(1, 1, 3), z(1, 1, 3)).tolist() == [[[0, 0, 0]]]

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
 }
 
 template <int NBL>
-__global__ void __launch_bounds__(256) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
+__global__ void __launch_bounds__(256, 6) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
                                                                 const float* __restrict__ ws, int Nq, int npad, int nblk,
                                                                 float* __restrict__ dist, int* __restrict__ idx) {
     // survivors of a block from which the sort-merge beats one-by-one insertion (measured: 6 for <= 64 blocks, 10-16 above)

@@ -824,12 +824,75 @@ seg_softmax_sum_kernel(const float* __restrict__ logit, const float* __restrict_
     }
 }
 
+// C == 64: a row is 256 bytes = 16 lanes x 16 bytes, so the two half-warps take alternate rows of a segment (eight rows in
+// flight per step, half as many load instructions); the two partial sums are added at the end.  Fixed shape -> deterministic.
+__global__ void __launch_bounds__(256)
+seg_softmax_sum64_kernel(const float* __restrict__ logit, const float* __restrict__ val, const int* __restrict__ ws, int B,
+                         int L, int n_seg, float* __restrict__ out) {
+    constexpr int C = 64;
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+    if (j >= n_seg) return;
+    const int* off = ws + (size_t)b * (n_seg + 1);
+    const int* rows = ws + (size_t)B * (n_seg + 1) + (size_t)B * n_seg + (size_t)b * L;
+    const float* lg = logit + (size_t)b * L;
+    const float* v = val + (size_t)b * L * C;
+    const int lo = off[j], hi = off[j + 1];
+    float mx = -INFINITY;
+    for (int a = lo + lane; a < hi; a += 32) mx = fmaxf(mx, lg[rows[a]]);
+    mx = ssf_warp_max(mx);
+    float den = 0.f;
+    for (int base = lo; base < hi; base += 32) {
+        const int a = base + lane;
+        den += ssf_warp_sum(a < hi ? expf(lg[rows[a]] - mx) : 0.f);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = lo; base < hi; base += 32) {
+        const int a = base + lane;
+        int r_l = 0;
+        float w_l = 0.f;
+        if (a < hi) {
+            r_l = rows[a];
+            w_l = expf(lg[r_l] - mx) / den;
+        }
+        const int nb = min(32, hi - base);
+        for (int t0 = 0; t0 < nb; t0 += 8) {
+            float wv[4];
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + 2 * u + half;                       // this half-warp's u-th row of the step
+                const int tc = min(t, nb - 1);
+                const int r = __shfl_sync(0xffffffffu, r_l, tc);
+                const float w = __shfl_sync(0xffffffffu, w_l, tc);
+                wv[u] = t < nb ? w : 0.f;
+                x[u] = __ldg(reinterpret_cast<const float4*>(v + (size_t)r * C) + l16);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc.x += x[u].x * wv[u];
+                acc.y += x[u].y * wv[u];
+                acc.z += x[u].z * wv[u];
+                acc.w += x[u].w * wv[u];
+            }
+        }
+    }
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    if (half == 0) reinterpret_cast<float4*>(out + ((size_t)b * n_seg + j) * C)[l16] = acc;
+}
+
 extern "C" int ssf_segment_softmax_sum(const float* logit, const float* val, const int* csr_ws, int B, int L, int C,
                                        int n_seg, float* out, void* stream) {
     if (B <= 0 || L <= 0 || C <= 0 || n_seg <= 0) return ssf_arg_error("segment_softmax_sum: empty input");
     if (C > 256) return ssf_arg_error("segment_softmax_sum: at most 256 channels");
     dim3 grid((n_seg + 7) / 8, B);
-    if (C % 2 == 0 && (reinterpret_cast<uintptr_t>(val) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
+    if (C == 64 && (reinterpret_cast<uintptr_t>(val) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        seg_softmax_sum64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logit, val, csr_ws, B, L, n_seg, out);
+    else if (C % 2 == 0 && (reinterpret_cast<uintptr_t>(val) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
         seg_softmax_sum_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(logit, val, csr_ws, B, L, C, n_seg, out);
     else
         seg_softmax_sum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(logit, val, csr_ws, B, L, C, n_seg, out);

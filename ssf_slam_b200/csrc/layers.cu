@@ -261,6 +261,7 @@ extern "C" int ssf_transpose(const float* in, int B, int R, int C, float* out, v
 //   mode 0: out = clamp(v, +-clampv)          (UpsampleFlow, clampv = 100)
 //   mode 1: out = clamp(q - v, +-clampv)      (PointWarping,  clampv = 10, C == 3)
 // query [B,N,3], src_pos [B,M,3], src_val [B,M,C], idx [B,N,k] -> out [B,N,C]; k <= 16
+template <int VEC>
 __global__ void __launch_bounds__(128)
 interpolate_kernel(const float* __restrict__ query, const float* __restrict__ src_pos, const float* __restrict__ src_val,
                    const int* __restrict__ idx, int ld_idx, int N, int M, int C, int k, int mode, float clampv,
@@ -283,6 +284,37 @@ interpolate_kernel(const float* __restrict__ query, const float* __restrict__ sr
     float norm = 0.f;
     for (int j = 0; j < k; ++j) norm += __shfl_sync(0xffffffffu, inv, j);  // slot order, as torch.sum over the last dim
     const float w = inv / norm;
+    if (VEC > 1) {
+        // C % VEC == 0, mode 0: every lane owns VEC consecutive channels (8- or 16-byte loads; 64 channels = one pass)
+        for (int c0 = 0; c0 < C; c0 += 32 * VEC) {
+            const int c = c0 + lane * VEC;
+            float v[VEC];
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) v[u] = 0.f;
+            for (int j = 0; j < k; ++j) {
+                const float wj = __shfl_sync(0xffffffffu, w, j);
+                const int ij = __shfl_sync(0xffffffffu, id, j);
+                if (c < C) {
+                    const float* sp = src_val + ((size_t)b * M + ij) * C + c;
+                    if (VEC == 2) {
+                        const float2 x = __ldg(reinterpret_cast<const float2*>(sp));
+                        v[0] += wj * x.x; v[1] += wj * x.y;
+                    } else {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(sp));
+                        v[0] += wj * x.x; v[1] += wj * x.y; v[VEC - 2] += wj * x.z; v[VEC - 1] += wj * x.w;
+                    }
+                }
+            }
+            if (c < C) {
+                float* op = out + ((size_t)b * N + n) * C + c;
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) v[u] = fminf(fmaxf(v[u], -clampv), clampv);
+                if (VEC == 2) *reinterpret_cast<float2*>(op) = make_float2(v[0], v[1]);
+                else *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[VEC - 2], v[VEC - 1]);
+            }
+        }
+        return;
+    }
     for (int c0 = 0; c0 < C; c0 += 32) {  // warp-uniform trip count: every lane takes part in the shuffles
         const int c = c0 + lane;
         float v = 0.f;
@@ -304,7 +336,13 @@ extern "C" int ssf_interpolate(const float* query, const float* src_pos, const f
     if (k <= 0 || k > 16 || ld_idx < k) return ssf_arg_error("interpolate: k must be in [1,16] and ld_idx >= k");
     if (mode == 1 && C != 3) return ssf_arg_error("interpolate: warp mode needs C == 3");
     dim3 grid((N + 3) / 4, B);
-    interpolate_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, mode, clampv, out);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(src_val) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (mode == 0 && C % 128 == 0 && al16)
+        interpolate_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, mode, clampv, out);
+    else if (mode == 0 && C % 64 == 0 && al16)
+        interpolate_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, mode, clampv, out);
+    else
+        interpolate_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, mode, clampv, out);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

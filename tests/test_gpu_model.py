@@ -300,3 +300,18 @@ def test_tflow_four_channel_input_variant_vs_reference_golden(golden_dir):
     b, _ = base(pc1, pc2, pc1, None)       # one of the two missing -> coordinates are used
     c, _ = base(pc1, pc2, pc1, pc2)        # both given and equal to the coordinates -> same result
     assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0])
+
+
+@pytest.mark.parametrize("C,k", [(3, 5), (64, 7), (128, 5), (256, 3), (96, 3), (64, 3)])
+def test_upsample_flow_channel_widths(C, k):
+    """UpsampleFlow (inverse-distance interpolation) at every channel width of the network: scalar path (C = 3, 96), 8-byte
+    (C = 64) and 16-byte (C = 128, 256) channel vectors per lane, against the oracle's restatement of soflow.py:1443-1475."""
+    from ssf_slam_b200 import model as M
+    g = torch.Generator().manual_seed(C + k)
+    xyz = torch.randn(2, 700, 3, generator=g) * 10
+    sparse = torch.randn(2, 200, 3, generator=g) * 10
+    val = torch.randn(2, 200, C, generator=g)
+    got = M.upsample_pm(xyz.cuda(), sparse.cuda(), val.cuda(), k).cpu()
+    want = tp.upsample_flow(xyz.transpose(1, 2).contiguous(), sparse.transpose(1, 2).contiguous(), val.transpose(1, 2).contiguous(), k)
+    assert got.shape == (2, 700, C)
+    assert float((got - want.transpose(1, 2)).abs().max()) < 2e-5

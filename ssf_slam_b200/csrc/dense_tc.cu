@@ -2,16 +2,18 @@
 // ASF/utils/soflow.py:397-451,460-461,501-513): Y[rows, N] = epilogue(A[rows, K] . W[N, K]^T) on tcgen05
 // `kind::tf32` with the fp32-faithful 3xTF32 split (tc_common.cuh), fp32 accumulators in TMEM.
 //
-// Persistent kernel: grid = (min(row tiles, SMs), column tiles of <= 256); every CTA walks 128-row tiles.  Roles:
+// Persistent kernel: grid = (min(row tiles, SMs), column tiles of <= 256); every CTA walks 128-row tiles.  Roles of the base
+// variant (the other role layouts -- wide, full, light -- are described at the kernel template below):
 //   warps 0-3 / 4-7  two A-producer warpgroups (thread = row = TMEM lane) taking alternate tiles.  A is streamed in
 //                    K chunks of 32: either plain rows of one or two concatenated inputs, or the *grouped first layer*
 //                    evaluated on the fly,
 //                       A[(b,n,s), c] = act1(G[b, idx[b,n,s], offG + c] + H[b, n, offH + c] + b1[c] + Wd1[:, c] . dir),
 //                    so a gathered neighbourhood never exists in HBM.  Each chunk is split into (hi, lo) TF32 halves and
-//                    written to a ring of TMEM stages with tcgen05.st.  Neighbour indices, positions and the next
-//                    chunk's rows are prefetched one step ahead in registers.
+//                    written to a ring of TMEM stages with tcgen05.st.  The rows come in by cp.async, two chunks ahead,
+//                    through a warp-private ring of staging tiles; neighbour indices and positions one tile ahead.
 //   warps 8-11       epilogue (thread = row): tcgen05.ld of the accumulator, then
-//                       STORE: y[row, :] = act(D + bias [+ Hq[row / S] + Wd2 . dir(row)])
+//                       STORE: y[row, :] = act(D + bias [+ Hq[row / S] + Wd2 . dir(row)])   (staged through shared memory so
+//                              that full 128-byte row segments leave per store instruction)
 //                       MAX  : y[row / S, :] = max over the S rows of a point (S in {8, 16}; butterfly over lanes)
 //                       DOT  : y[row] = wvec . act(D + bias) + b0                      (weightnet1's last conv)
 //   warp 12          one thread issues the MMAs (12 per chunk: 3 passes x 4 K-steps of 8)

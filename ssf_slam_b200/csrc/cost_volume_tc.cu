@@ -11,7 +11,9 @@
 // Per tile each branch runs five GEMMs (mlp_convs[1] | mlp_convs3[0] | mlp_convs3[1] | weightnet1[0] | weightnet1[3]);
 // the two branches alternate on the tensor pipe so one branch's epilogue overlaps the other's MMAs, and the S x S
 // attention (CUDA cores, packed fp32x2 FMAs, activations exchanged through shared memory) overlaps the mlp_convs3[0] MMAs.
-// Gathers and the Cw store go through a shared-memory transpose so that every global access is a full 128-byte line.
+// Gathers and the Cw store go through a shared-memory transpose so that every global access is a full 128-byte line; the
+// gathered rows of the NEXT tile are fetched by cp.async as soon as the staging sub-tile is free.  Epilogue bias / direction /
+// activation math runs on packed fp32x2 instructions.
 // TMEM columns: IN_a hi|lo 0..127, IN_w hi|lo 128..255, D_a 256, D_w 320, C_a 384, C_w 448 (64 fp32 columns each).
 #include "tc_common.cuh"
 

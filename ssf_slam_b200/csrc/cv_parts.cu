@@ -12,8 +12,9 @@ __global__ void __launch_bounds__(256) attention_mix_kernel(const float* __restr
     const int ld = m + 4;
     float* sA = sm;                 // [16][ld]
     float* sW = sA + 16 * ld;       // [16][ld]
-    float* sQ = sW + 16 * ld;       // [16][17]
-    float* sStat = sQ + 16 * 17;    // row max | row sum | col max | col sum, [16] each
+    float* sQ = sW + 16 * ld;       // [16][LQ]
+    constexpr int LQ = 20;          // row stride of sQ: 16-byte aligned rows
+    float* sStat = sQ + 16 * LQ;    // row max | row sum | col max | col sum, [16] each
     const int tid = threadIdx.x;
     const size_t base = (size_t)blockIdx.x * 16 * m;
     const int q4 = m >> 2;
@@ -23,53 +24,82 @@ __global__ void __launch_bounds__(256) attention_mix_kernel(const float* __restr
         *reinterpret_cast<float4*>(sW + r * ld + c) = __ldg(reinterpret_cast<const float4*>(Aw + base + (size_t)r * m + c));
     }
     __syncthreads();
-    {
-        const int i = tid >> 4, j = tid & 15;
-        const float* ar = sA + i * ld;
-        const float* wr = sW + j * ld;
-        float s = 0.f;
-        for (int c = 0; c < m; c += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(ar + c);
-            const float4 y = *reinterpret_cast<const float4*>(wr + c);
-            s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    {   // Q[i][j] = <A_i, Aw_j>: thread = 2 x 2 block over a quarter of the channels (every value read from shared memory
+        // feeds two FMAs: the kernel is bound by shared-memory bandwidth), partial sums combined over the 4 slices by shuffles
+        const int blk = tid >> 2, ks = tid & 3, bi = blk >> 3, bj = blk & 7;
+        const float* a0 = sA + (2 * bi) * ld, *a1 = a0 + ld;
+        const float* w0 = sW + (2 * bj) * ld, *w1 = w0 + ld;
+        float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+        for (int c = ks * 4; c < m; c += 16) {   // slice ks owns the channel quads ks, ks + 4, ...
+            const float4 x0 = *reinterpret_cast<const float4*>(a0 + c), x1 = *reinterpret_cast<const float4*>(a1 + c);
+            const float4 y0 = *reinterpret_cast<const float4*>(w0 + c), y1 = *reinterpret_cast<const float4*>(w1 + c);
+            s00 = fmaf(x0.x, y0.x, s00); s00 = fmaf(x0.y, y0.y, s00); s00 = fmaf(x0.z, y0.z, s00); s00 = fmaf(x0.w, y0.w, s00);
+            s01 = fmaf(x0.x, y1.x, s01); s01 = fmaf(x0.y, y1.y, s01); s01 = fmaf(x0.z, y1.z, s01); s01 = fmaf(x0.w, y1.w, s01);
+            s10 = fmaf(x1.x, y0.x, s10); s10 = fmaf(x1.y, y0.y, s10); s10 = fmaf(x1.z, y0.z, s10); s10 = fmaf(x1.w, y0.w, s10);
+            s11 = fmaf(x1.x, y1.x, s11); s11 = fmaf(x1.y, y1.y, s11); s11 = fmaf(x1.z, y1.z, s11); s11 = fmaf(x1.w, y1.w, s11);
         }
-        sQ[i * 17 + j] = s;
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            s00 += __shfl_xor_sync(0xffffffffu, s00, o);
+            s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+            s10 += __shfl_xor_sync(0xffffffffu, s10, o);
+            s11 += __shfl_xor_sync(0xffffffffu, s11, o);
+        }
+        if (ks == 0) {
+            sQ[(2 * bi) * LQ + 2 * bj] = s00;
+            sQ[(2 * bi) * LQ + 2 * bj + 1] = s01;
+            sQ[(2 * bi + 1) * LQ + 2 * bj] = s10;
+            sQ[(2 * bi + 1) * LQ + 2 * bj + 1] = s11;
+        }
     }
     __syncthreads();
     if (tid < 32) {
         const int which = tid >> 4, t = tid & 15;   // 0: row t (over j), 1: column t (over i)
         float mx = -INFINITY;
-        for (int u = 0; u < 16; ++u) mx = fmaxf(mx, which == 0 ? sQ[t * 17 + u] : sQ[u * 17 + t]);
+        for (int u = 0; u < 16; ++u) mx = fmaxf(mx, which == 0 ? sQ[t * LQ + u] : sQ[u * LQ + t]);
         float sum = 0.f;
-        for (int u = 0; u < 16; ++u) sum += expf((which == 0 ? sQ[t * 17 + u] : sQ[u * 17 + t]) - mx);
+        for (int u = 0; u < 16; ++u) sum += expf((which == 0 ? sQ[t * LQ + u] : sQ[u * LQ + t]) - mx);
         sStat[which * 32 + t] = mx;
         sStat[which * 32 + 16 + t] = sum;
     }
     __syncthreads();
     {
         const int i = tid >> 4, j = tid & 15;
-        const float q = sQ[i * 17 + j];
+        const float q = sQ[i * LQ + j];
         const float over_j = expf(q - sStat[i]) / sStat[16 + i];
         const float over_i = expf(q - sStat[32 + j]) / sStat[48 + j];
         __syncthreads();
-        sQ[i * 17 + j] = over_j * over_i;
+        sQ[i * LQ + j] = over_j * over_i;
     }
     __syncthreads();
-    for (int e = tid; e < 16 * q4; e += 256) {
-        const int r = e / q4, c = (e % q4) * 4;
-        float4 a = *reinterpret_cast<const float4*>(sA + r * ld + c);
-        float4 w = *reinterpret_cast<const float4*>(sW + r * ld + c);
+    // mixes: thread = 4 rows x one channel quad, so that every row of the other branch read from shared memory feeds the four
+    // rows at once (A'_r += Q[r][u] Aw_u, Aw'_r += Q[u][r] A_u)
+    for (int e = tid; e < 4 * q4; e += 256) {
+        const int r0 = (e / q4) * 4, c = (e % q4) * 4;
+        float4 a[4], w[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            a[x] = *reinterpret_cast<const float4*>(sA + (r0 + x) * ld + c);
+            w[x] = *reinterpret_cast<const float4*>(sW + (r0 + x) * ld + c);
+        }
 #pragma unroll 4
         for (int u = 0; u < 16; ++u) {
-            const float qa = sQ[r * 17 + u];   // Q[r][u]  : A'_r  += Q[r][u] * Aw_u
-            const float qw = sQ[u * 17 + r];   // Q[u][r]  : Aw'_r += Q[u][r] * A_u
             const float4 ow = *reinterpret_cast<const float4*>(sW + u * ld + c);
             const float4 oa = *reinterpret_cast<const float4*>(sA + u * ld + c);
-            a.x = fmaf(qa, ow.x, a.x); a.y = fmaf(qa, ow.y, a.y); a.z = fmaf(qa, ow.z, a.z); a.w = fmaf(qa, ow.w, a.w);
-            w.x = fmaf(qw, oa.x, w.x); w.y = fmaf(qw, oa.y, w.y); w.z = fmaf(qw, oa.z, w.z); w.w = fmaf(qw, oa.w, w.w);
+            const float4 qw4 = *reinterpret_cast<const float4*>(sQ + u * LQ + r0);   // Q[u][r0 .. r0 + 3]
+            const float qw[4] = {qw4.x, qw4.y, qw4.z, qw4.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float qa = sQ[(r0 + x) * LQ + u];                              // Q[r0 + x][u]
+                a[x].x = fmaf(qa, ow.x, a[x].x); a[x].y = fmaf(qa, ow.y, a[x].y); a[x].z = fmaf(qa, ow.z, a[x].z); a[x].w = fmaf(qa, ow.w, a[x].w);
+                w[x].x = fmaf(qw[x], oa.x, w[x].x); w[x].y = fmaf(qw[x], oa.y, w[x].y); w[x].z = fmaf(qw[x], oa.z, w[x].z); w[x].w = fmaf(qw[x], oa.w, w[x].w);
+            }
         }
-        *reinterpret_cast<float4*>(Amix + base + (size_t)r * m + c) = a;
-        *reinterpret_cast<float4*>(Awmix + base + (size_t)r * m + c) = w;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            *reinterpret_cast<float4*>(Amix + base + (size_t)(r0 + x) * m + c) = a[x];
+            *reinterpret_cast<float4*>(Awmix + base + (size_t)(r0 + x) * m + c) = w[x];
+        }
     }
 }
 
@@ -77,7 +107,7 @@ extern "C" int ssf_attention_mix(const float* A, const float* Aw, long long n_po
                                  void* stream) {
     if (n_points <= 0) return ssf_arg_error("attention_mix: empty input");
     if (m % 4 || m > 512) return ssf_arg_error("attention_mix: m must be a multiple of 4, <= 512");
-    const size_t smem = (size_t)(2 * 16 * (m + 4) + 16 * 17 + 64) * sizeof(float);
+    const size_t smem = (size_t)(2 * 16 * (m + 4) + 16 * 20 + 64) * sizeof(float);
     attention_mix_kernel<<<(unsigned)n_points, 256, smem, (cudaStream_t)stream>>>(A, Aw, m, Amix, Awmix);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();

@@ -826,7 +826,7 @@ __global__ void csr_fill_kernel(const IdxT* __restrict__ key, int L, int n_seg, 
 }
 
 // rows of every segment into ascending order (the fill above lands them in atomic order).  One warp per segment:
-// segments of <= 32 rows (the common case: 16 on average) are sorted across the lanes by a bitonic network, longer ones
+// segments of <= 32 rows (the common case: 16 on average) are sorted across the lanes by ranking, longer ones
 // by an insertion sort on lane 0.
 __global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ offset, int n_seg, int L, int* __restrict__ rows) {
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -838,17 +838,13 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ o
     const int lo = off[j], hi = off[j + 1], cnt = hi - lo;
     if (cnt <= 1) return;
     if (cnt <= 32) {
-        int v = lane < cnt ? r[lo + lane] : 0x7fffffff;
-#pragma unroll
-        for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                const int o = __shfl_xor_sync(0xffffffffu, v, jj);
-                const bool take_min = ((lane & jj) == 0) == ((lane & kk) == 0);
-                v = take_min ? min(v, o) : max(v, o);
-            }
-        }
-        if (lane < cnt) r[lo + lane] = v;
+        // rank sort: the rows of a segment are distinct, so a row's place is the number of smaller rows.  The cnt broadcasts
+        // are independent of each other (a bitonic network is a chain of 15 dependent shuffles)
+        const int v = lane < cnt ? r[lo + lane] : 0x7fffffff;
+        int rank = 0;
+        for (int u = 0; u < cnt; ++u) rank += __shfl_sync(0xffffffffu, v, u) < v ? 1 : 0;
+        __syncwarp();
+        if (lane < cnt) r[lo + rank] = v;
     } else if (lane == 0) {
         for (int a = lo + 1; a < hi; ++a) {
             const int v = r[a];

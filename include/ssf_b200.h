@@ -157,6 +157,11 @@ int ssf_frontend(const float* points, const float* flow, int B, int N, int mode,
                  const int* sem, unsigned long long movable_bits, const int* inst, int n_inst, float tau,
                  unsigned char* mask_out, double* odom_out, double* pose_out, void* stream);
 
+/* slove_RT_by_SVD(src[M,3], dst[M,3]) -> dst ~= R src + t (scripts/PointCloudOdometry.py:15-33) for float64 clouds, computed in
+ * float64 like the reference computes in its input dtype.  src, dst f64 [B,M,3] -> odom f64 [B,7], pose f64 [B,12] = [R | t].
+ * Fewer than 3 points -> identity. */
+int ssf_solve_rt_f64(const double* src, const double* dst, int B, int M, double* odom_out, double* pose_out, void* stream);
+
 /* ---- the reference's noSeg masker on the device: 2-component full-covariance Gaussian mixture by EM on [flow | xyz],
  * majority component = background.  Replaces `GaussianMixture(n_components=2).fit_predict(...)` + `Counter.most_common(1)` at
  * scripts/PointCloudOdometry_noSeg.py:97-103 and ASF/main_sju_occ_ros.py:257-263 (scikit-learn defaults: tol 1e-3, reg_covar
@@ -167,12 +172,6 @@ int ssf_frontend(const float* points, const float* flow, int B, int N, int mode,
 int ssf_gmm_mask(const float* points, const float* flow, int B, int N, int max_iter, double tol, unsigned char* mask_out,
                  double* info_out, void* stream);
 
-/* ---- tensor-core bring-up / regression: Y[128,N] = X[128,K].W[N,K]^T on tcgen05 kind::tf32 (3xTF32 when passes == 3);
- * Whi_img / Wlo_img are the split weights in the no-swizzle K-major UMMA image (ssf_slam_b200.tc.weight_image);
- * mode 0: A operand from TMEM, mode 1: A operand from shared memory */
-int ssf_tc_gemm_test(const float* X, const float* Whi_img, const float* Wlo_img, int K, int N, int mode, int passes,
-                     float* Y, void* stream);
-
 /* ---- next after the path: plane-feature extraction of the back end's first node, src/frameFeature.cpp:45-127
  * (scan-line id from elevation, stable regrouping per line, 11-tap curvature, greedy selection curvature < plane_min with a
  * skip of plane_span).  points [B,N,3] -> out [B,N,4] = (x, y, z, intensity = indexInRow + line/100), out_count [B].
@@ -180,10 +179,6 @@ int ssf_tc_gemm_test(const float* X, const float* Whi_img, const float* Wlo_img,
 long long ssf_plane_features_workspace_bytes(int B, int N);
 int ssf_plane_features(const float* points, int B, int N, int n_rows, int row_start, int row_end, float plane_min,
                        int plane_span, void* ws, float* out, int* out_count, void* stream);
-
-/* tensor-pipe pacing probe (developer tool): cycles for `reps` back-to-back M128 x N x K8 kind::tf32 MMAs, A operand from
- * TMEM (mode 0) or shared memory (mode 1), acc_bufs accumulators round-robin; out[0] = total cycles, out[1] = issue cycles */
-int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,19 +32,19 @@ from ssf_slam_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def gen_tflow(n_points, data_seed, weight_seed=0, flow_channels=3):
+def gen_tflow(n_points, data_seed, weight_seed=0, flow_channels=3, with_labels=False):
     """flow_channels=4: the reference with its source flag ``add_Seg_after_FLow`` (utils/datasets/carla.py:9, imported by
     name into utils/soflow.py:8) switched on for the duration of the call -- 4-channel flow heads."""
     TFlow = import_reference_tflow()
     import utils.soflow as ref_soflow  # the reference module whose global the classes read
     ref_soflow.add_Seg_after_FLow = flow_channels == 4
     try:
-        _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels)
+        _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels, with_labels)
     finally:
         ref_soflow.add_Seg_after_FLow = False
 
 
-def _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels):
+def _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels, with_labels=False):
     sd = tflow_port.random_init_state_dict(weight_seed, flow_channels)
     net = TFlow().eval()
     net.load_state_dict(sd, strict=True)
@@ -59,7 +59,8 @@ def _gen_tflow(TFlow, n_points, data_seed, weight_seed, flow_channels):
     for a, b in zip(fps, pfps):
         assert torch.equal(a, b), "oracle port FPS deviates from the reference"
     name = "tflow_n%d.npz" % n_points if flow_channels == 3 else "tflow_seg4_n%d.npz" % n_points
-    np.savez_compressed(os.path.join(OUT, name), pos1=item["pos1"], pos2=item["pos2"],
+    extra = dict(sem=item["sem"], inst=item["inst"]) if with_labels else {}   # config 3 (Seg pipeline): synthetic labels
+    np.savez_compressed(os.path.join(OUT, name), pos1=item["pos1"], pos2=item["pos2"], **extra,
                         flow0=flows[0][0].numpy(), flow1=flows[1][0].numpy(), flow2=flows[2][0].numpy(),
                         flow3=flows[3][0].numpy(), fps1=fps[0][0].numpy(), fps2=fps[1][0].numpy(), fps3=fps[2][0].numpy(),
                         weight_seed=weight_seed, data_seed=data_seed, flow_channels=flow_channels)
@@ -171,3 +172,4 @@ if __name__ == "__main__":
     gen_tflow(8192, data_seed=0)
     gen_tflow(2048, data_seed=43, flow_channels=4)
     gen_tflow_afterpc(2048, data_seed=44)
+    gen_tflow(16384, data_seed=3000, with_labels=True)   # BASELINE config 3 size

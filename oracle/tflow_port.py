@@ -252,11 +252,13 @@ def tflow_forward(sd, pc1, pc2, return_intermediates=False, feats1=None, feats2=
     cf, cb, ff, flow = refine_flow(sd, "flow3_r", 16, False, pcs1[3], pcs2[3], u1, u2, 3)
     flows = [flow]
     inter["l3"] = (cf, cb, ff, flow)
+    inter["in3"] = dict(u1=u1, u2=u2)
 
     # levels 2, 1, 0: (su, flow regressor, deconv, k for flow/feat upsample, warp k)
     for lvl, su, fr, dc, k_up, k_warp in ((2, "su2", "flow2_r", "deconv3_2", 5, 5),
                                          (1, "su1", "flow1_r", "deconv2_1", 5, 7),
                                          (0, "su0", "flow0_r", "deconv1_0", 7, 7)):
+        prev1, prev2 = u1, u2
         u1 = set_upconv(sd, su, 16, pcs1[lvl], pcs1[lvl + 1], f1[lvl], u1)
         u2 = set_upconv(sd, su, 16, pcs2[lvl], pcs2[lvl + 1], f2[lvl], u2)
         coarse = upsample_flow(pcs1[lvl], pcs1[lvl + 1], flow, k=k_up)
@@ -268,6 +270,9 @@ def tflow_forward(sd, pc1, pc2, return_intermediates=False, feats1=None, feats2=
         cf, cb, ff, flow = refine_flow(sd, fr, 16, True, pcs1[lvl], pcs2[lvl], in1, in2, k_warp, coarse, sf_feat)
         flows.append(flow)
         inter["l%d" % lvl] = (cf, cb, ff, flow)
+        # what each layer of this level was fed (teacher forcing in the parity tests)
+        inter["in%d" % lvl] = dict(prev1=prev1, prev2=prev2, u1=u1, u2=u2, coarse=coarse, sf_feat=sf_feat, cfu=cfu, cbu=cbu,
+                                   su=su, fr=fr, dc=dc, k_up=k_up, k_warp=k_warp)
 
     out = (flows[::-1], fps[:3])
     if return_intermediates:

@@ -11,7 +11,7 @@ def run(X, W, mode, passes):
     hi, lo = tc.weight_image(W)
     Y = torch.full((128, N), float("nan"), device="cuda")
     Xd, hid, lod = X.cuda().contiguous(), hi.cuda(), lo.cuda()
-    nat.check(nat.lib().ssf_tc_gemm_test(nat.ptr(Xd), nat.ptr(hid), nat.ptr(lod), K, N, mode, passes, nat.ptr(Y), nat.stream()))
+    nat.check(nat.dev_lib().ssf_tc_gemm_test(nat.ptr(Xd), nat.ptr(hid), nat.ptr(lod), K, N, mode, passes, nat.ptr(Y), nat.stream()), nat.dev_lib())
     torch.cuda.synchronize()
     return Y.cpu()
 

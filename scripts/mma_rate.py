@@ -11,7 +11,7 @@ for N in (32, 64, 128, 256):
             if bufs * N > 480:
                 continue
             reps = 2000
-            nat.check(nat.lib().ssf_tc_mma_rate(N, mode, reps, bufs, nat.ptr(out), nat.stream()))
+            nat.check(nat.dev_lib().ssf_tc_mma_rate(N, mode, reps, bufs, nat.ptr(out), nat.stream()), nat.dev_lib())
             torch.cuda.synchronize()
             t = out.cpu().tolist()
             print("N=%3d A-from-%s acc_bufs=%d: %.1f cycles/MMA total, %.1f issue" % (N, ("TMEM", "smem", "TMEM/uniform-issue", "smem/uniform-issue")[mode], bufs, t[0] / reps, t[1] / reps))

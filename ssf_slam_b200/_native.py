@@ -6,6 +6,7 @@ a non-sm_100 device raises.
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -54,9 +55,16 @@ SIGNATURES = {
     "ssf_dense_args_bytes": ("", _I),
     "ssf_dense_set_variant": ("i", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
+    "ssf_solve_rt_f64": ("ppiippp", _I),
     "ssf_gmm_mask": ("ppiiidppp", _I),
     "ssf_plane_features_workspace_bytes": ("ii", _I64),
     "ssf_plane_features": ("piiiiifipppp", _I),
+}
+
+# developer library (csrc/dev/ssf_b200_dev.h -> libssf_b200_dev.so): bring-up / probe kernels kept out of the product ABI
+DEV_LIB_PATH = os.path.join(_HERE, "libssf_b200_dev.so")
+DEV_SIGNATURES = {
+    "ssf_last_error": ("", ctypes.c_char_p),
     "ssf_tc_gemm_test": ("pppiiiipp", _I),
     "ssf_tc_mma_rate": ("iiiipp", _I),
 }
@@ -76,6 +84,30 @@ class DenseArgs(ctypes.Structure):
 
 
 _lib = None
+_tls = threading.local()
+
+
+def _wrap(fn):
+    """Launch on the device that owns the tensors of the call (recorded by ``ptr``), not on whatever device happens to be
+    current: kernels, their stream and the per-device function attributes all follow the data (``device='cuda:1'`` arguments,
+    nn.DataParallel replicas).  One device per call; mixing devices raises."""
+    def call(*args):
+        devs = getattr(_tls, "devs", None)
+        _tls.devs = None
+        if devs:
+            if len(devs) > 1:
+                raise SsfError("tensors of one call live on different devices: %s" % sorted(devs))
+            dev = next(iter(devs))
+            if dev != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    return fn(*args)
+        return fn(*args)
+    call.__name__ = fn.__name__
+    return call
+
+
+class _Lib:
+    pass
 
 
 def lib():
@@ -86,35 +118,64 @@ def lib():
             raise RuntimeError("%s is missing: run `python -m ssf_slam_b200.build` (or __graft_entry__.build()); "
                                "ssf_slam_b200 has no CPU fallback" % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
+        ns = _Lib()
         for name, (codes, res) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = [_CODES[c] for c in codes]
             fn.restype = res
-        _lib = L
+            setattr(ns, name, _wrap(fn) if "p" in codes else fn)
+        _lib = ns
     return _lib
+
+
+_dev_lib = None
+
+
+def dev_lib():
+    """The developer library (tests / scripts only; the product never loads it)."""
+    global _dev_lib
+    if _dev_lib is None:
+        L = ctypes.CDLL(DEV_LIB_PATH)
+        ns = _Lib()
+        for name, (codes, res) in DEV_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = [_CODES[c] for c in codes]
+            fn.restype = res
+            setattr(ns, name, _wrap(fn) if "p" in codes else fn)
+        _dev_lib = ns
+    return _dev_lib
 
 
 class SsfError(RuntimeError):
     pass
 
 
-def check(rc):
+def check(rc, library=None):
     if rc != 0:
-        raise SsfError(lib().ssf_last_error().decode())
+        raise SsfError((library or lib()).ssf_last_error().decode())
 
 
 def ptr(t):
-    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    """Device pointer of a contiguous CUDA tensor (None -> NULL).  Notes the tensor's device for the launch (see _wrap)."""
     if t is None:
         return None
     if not t.is_cuda:
         raise SsfError("ssf_slam_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
     if not t.is_contiguous():
         raise SsfError("tensor must be contiguous")
+    devs = getattr(_tls, "devs", None)
+    if devs is None:
+        devs = _tls.devs = set()
+    devs.add(t.device.index)
     return t.data_ptr()
 
 
 def stream():
+    """The current torch stream of the device the call's tensors live on (arguments are evaluated left to right and the stream
+    comes last in every signature, so every ``ptr`` of the call has run)."""
+    devs = getattr(_tls, "devs", None)
+    if devs:
+        return torch.cuda.current_stream(next(iter(devs))).cuda_stream
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -122,13 +183,17 @@ def launch_count():
     return int(lib().ssf_launch_count())
 
 
-_device_ok = False
+_devices_ok = set()
 
 
-def require_device():
-    global _device_ok
-    if not _device_ok:
-        if not torch.cuda.is_available():
-            raise SsfError("no CUDA device: ssf_slam_b200 runs on B200 (sm_100a) only")
-        check(lib().ssf_require_device())
-        _device_ok = True
+def require_device(device=None):
+    """Raises unless ``device`` (default: the current device) is an sm_100 GPU; checked once per device."""
+    if not torch.cuda.is_available():
+        raise SsfError("no CUDA device: ssf_slam_b200 runs on B200 (sm_100a) only")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _devices_ok:
+        with torch.cuda.device(idx):
+            check(lib().ssf_require_device())
+        _devices_ok.add(idx)

@@ -9,6 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libssf_b200.so")
+DEV_LIB = os.path.join(HERE, "libssf_b200_dev.so")   # developer entry points (csrc/dev/), not part of the product ABI
 OBJ_DIR = os.path.join(HERE, "build")
 NVCC_FLAGS = (["-DSSF_CV_TRACE"] if os.environ.get("SSF_CV_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", os.path.join(os.path.dirname(HERE), "include")]
@@ -18,8 +19,12 @@ def sources():
     return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
 
 
+def dev_sources():
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "dev", "*.cu")))
+
+
 def headers():
-    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "dev", "*.h")) + glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
 
 
 def _obj(src):
@@ -34,7 +39,7 @@ def _stale(target, deps):
 
 
 def needs_build():
-    return _stale(LIB, sources() + headers())
+    return _stale(LIB, sources() + headers()) or _stale(DEV_LIB, dev_sources() + headers())
 
 
 def _nvcc():
@@ -54,11 +59,13 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdrs = headers()
-    todo = [s for s in sources() if force or _stale(_obj(s), [s] + hdrs)]
+    todo = [s for s in sources() + dev_sources() if force or _stale(_obj(s), [s] + hdrs)]
     extra = ["-Xptxas", "-v"] if verbose else []
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as ex:
         list(ex.map(lambda s: _run([_nvcc()] + NVCC_FLAGS + extra + ["-c", s, "-o", _obj(s)], verbose), todo))
     _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(s) for s in sources()], verbose)
+    capi = [_obj(s) for s in sources() if os.path.basename(s) == "capi.cu"]   # error / launch-count plumbing (own copy)
+    _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", DEV_LIB] + [_obj(s) for s in dev_sources()] + capi, verbose)
     return LIB
 
 

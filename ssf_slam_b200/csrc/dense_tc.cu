@@ -639,14 +639,14 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     const bool full_r = light_mode && !light && a.a_mode == 0 && cfg.Nt == 64 && full_ok;
     const bool wide = light_mode && !light && !full_r && a.epi_mode != SSF_EPI_DOT && (cfg.Nt == 256 || (a.a_mode == 0 && cfg.Nt >= 64));
     cfg.nd = light ? 2 : ((2 * cfg.Nt + AS * 64 <= 512) ? 2 : 1);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (ssf_attr_needed(&attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIGHT_SMEM_MAX);
         if (e != cudaSuccess) return ssf_set_error(e);
-        attr_set = true;
+        ssf_attr_done(&attr_set);
     }
     const int n_cta = light ? 2 * 148 : 148;
     dim3 grid((unsigned)(cfg.n_tiles < n_cta ? cfg.n_tiles : n_cta), (unsigned)((a.N + 255) / 256));

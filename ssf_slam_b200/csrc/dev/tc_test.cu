@@ -1,7 +1,7 @@
 // Bring-up / regression kernel for the tcgen05 path: Y[128,N] = X[128,K] . W[N,K]^T with the 3xTF32 scheme,
 // exercising exactly the mechanisms the fused layers use (TMEM alloc, tcgen05.st of split activations, A-from-TMEM
 // and A-from-smem MMAs against pre-arranged weight images, commit -> mbarrier, tcgen05.ld epilogue).
-#include "tc_common.cuh"
+#include "../tc_common.cuh"
 
 // mode 0: A operand from TMEM; mode 1: A operand from shared memory (no-swizzle K-major image written by the threads)
 // passes 1: hi.hi only (plain TF32); 3: full 3xTF32

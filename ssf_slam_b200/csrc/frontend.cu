@@ -271,6 +271,50 @@ frontend_kernel(const float* __restrict__ points, const float* __restrict__ flow
     }
 }
 
+// slove_RT_by_SVD(src, dst) on float64 clouds, in the input precision like the reference (scripts/PointCloudOdometry.py:15-33
+// runs numpy in the dtype it is given): the same 16 fp64 sums and Horn closed form as above, fed with doubles.
+__global__ void __launch_bounds__(FE_T)
+solve_rt_f64_kernel(const double* __restrict__ src, const double* __restrict__ dst, int M, double* __restrict__ odom_out,
+                    double* __restrict__ pose_out) {
+    __shared__ double s_part[FE_T / 32][16];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* A = src + (size_t)b * M * 3;
+    const double* Bp = dst + (size_t)b * M * 3;
+    double acc[16];
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int i = tid; i < M; i += FE_T) {
+        const double a0 = A[3 * i], a1 = A[3 * i + 1], a2 = A[3 * i + 2];
+        const double b0 = Bp[3 * i], b1 = Bp[3 * i + 1], b2 = Bp[3 * i + 2];
+        acc[0] = xadd(acc[0], 1.0);
+        acc[1] = xadd(acc[1], a0); acc[2] = xadd(acc[2], a1); acc[3] = xadd(acc[3], a2);
+        acc[4] = xadd(acc[4], b0); acc[5] = xadd(acc[5], b1); acc[6] = xadd(acc[6], b2);
+        acc[7] = xadd(acc[7], xmul(a0, b0)); acc[8] = xadd(acc[8], xmul(a0, b1)); acc[9] = xadd(acc[9], xmul(a0, b2));
+        acc[10] = xadd(acc[10], xmul(a1, b0)); acc[11] = xadd(acc[11], xmul(a1, b1)); acc[12] = xadd(acc[12], xmul(a1, b2));
+        acc[13] = xadd(acc[13], xmul(a2, b0)); acc[14] = xadd(acc[14], xmul(a2, b1)); acc[15] = xadd(acc[15], xmul(a2, b2));
+    }
+    block_sum16(acc, s_part);
+    if (tid == 0) {
+        Pose pose;
+        pose_from_sums(acc, pose);
+        double* o = odom_out + (size_t)b * 7;
+        o[0] = pose.t[0]; o[1] = pose.t[1]; o[2] = pose.t[2];
+        o[3] = pose.q[1]; o[4] = pose.q[2]; o[5] = pose.q[3]; o[6] = pose.q[0];
+        double* p = pose_out + (size_t)b * 12;
+        for (int k = 0; k < 9; ++k) p[k] = pose.R[k];
+        for (int k = 0; k < 3; ++k) p[9 + k] = pose.t[k];
+    }
+}
+
+extern "C" int ssf_solve_rt_f64(const double* src, const double* dst, int B, int M, double* odom_out, double* pose_out,
+                                void* stream) {
+    if (B <= 0 || M <= 0) return ssf_arg_error("solve_rt_f64: empty input");
+    if (odom_out == nullptr || pose_out == nullptr) return ssf_arg_error("solve_rt_f64: outputs must not be NULL");
+    solve_rt_f64_kernel<<<B, FE_T, 0, (cudaStream_t)stream>>>(src, dst, M, odom_out, pose_out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
 // points, flow [B,N,3] f32; optional in_mask u8 [B,N] (mode 0), sem / inst i32 [B,N]
 // -> mask u8 [B,N], odom f64 [B,7] = [tx,ty,tz,qx,qy,qz,qw], pose f64 [B,12] = [R row-major, t] (may be null)
 extern "C" int ssf_frontend(const float* points, const float* flow, int B, int N, int mode, const unsigned char* in_mask,

@@ -407,11 +407,11 @@ extern "C" int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, 
     if (Nr > 16384) return ssf_arg_error("knn_blocks_build: at most 16384 reference points (larger clouds use ssf_knn)");
     const int npow2 = next_pow2(Nr), npad = (Nr + 31) / 32 * 32, nblk = npad / 32;
     const size_t smem = (size_t)npow2 * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (ssf_attr_needed(&attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(knn_blocks_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
         if (e != cudaSuccess) return ssf_set_error(e);
-        attr_set = true;
+        ssf_attr_done(&attr_set);
     }
     knn_blocks_build_kernel<<<B, KB_BUILD_T, smem, (cudaStream_t)stream>>>(ref, Nr, npow2, npad, nblk, ws);
     ssf_count_launch();

@@ -680,11 +680,11 @@ extern "C" int ssf_grouping_operation(const float* feat, const int* idx, int B, 
         const size_t smem = (size_t)N * 4 * STAGE_GC;
         int chunk4 = MS4;                                  // float4 outputs per CTA: at least N (4N outputs per channel)
         while (chunk4 / 2 >= N && chunk4 % 2 == 0) chunk4 /= 2;
-        static size_t attr = 0;
-        if (smem > attr) {
+        static unsigned long long attr = 0;
+        if (ssf_attr_needed(&attr)) {
             cudaError_t e = cudaFuncSetAttribute(group_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return ssf_set_error(e);
-            attr = 200 * 1024;
+            ssf_attr_done(&attr);
         }
         dim3 grid((MS4 + chunk4 - 1) / chunk4, (C + STAGE_GC - 1) / STAGE_GC, B);
         group_staged_kernel<<<grid, STAGE_T, smem, st>>>(feat, idx, C, N, MS4, chunk4, out);
@@ -739,12 +739,12 @@ extern "C" int ssf_three_interpolate(const float* feat, const int* idx, const fl
         const size_t smem = (size_t)M * 4 * gc;
         int chunk = N;
         while (chunk / 2 >= M && chunk % 2 == 0) chunk /= 2;
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (ssf_attr_needed(&attr)) {
             cudaError_t e = cudaFuncSetAttribute(three_interpolate_staged_kernel<2, STAGE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(three_interpolate_staged_kernel<3, STAGE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return ssf_set_error(e);
-            attr = true;
+            ssf_attr_done(&attr);
         }
         dim3 grid((N + chunk - 1) / chunk, (C + gc - 1) / gc, B);
         const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -827,7 +827,7 @@ __global__ void csr_fill_kernel(const IdxT* __restrict__ key, int L, int n_seg, 
 
 // rows of every segment into ascending order (the fill above lands them in atomic order).  One warp per segment:
 // segments of <= 32 rows (the common case: 16 on average) are sorted across the lanes by ranking, longer ones
-// by an insertion sort on lane 0.
+// by a warp-cooperative bitonic network in global memory.
 __global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ offset, int n_seg, int L, int* __restrict__ rows) {
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -845,15 +845,36 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ o
         for (int u = 0; u < cnt; ++u) rank += __shfl_sync(0xffffffffu, v, u) < v ? 1 : 0;
         __syncwarp();
         if (lane < cnt) r[lo + rank] = v;
-    } else if (lane == 0) {
-        for (int a = lo + 1; a < hi; ++a) {
-            const int v = r[a];
-            int p = a - 1;
-            while (p >= lo && r[p] > v) {
-                r[p + 1] = r[p];
-                --p;
+    } else {
+        // long segment (many queries share a neighbour, e.g. zero-padded returns piled on one point): warp-cooperative bitonic
+        // network in place, O(n log^2 n / 32) instead of a single lane's O(n^2) insertion sort.  All compare-exchanges are
+        // ascending (first step of every merge mirrored), so the virtual +inf padding up to a power of two stays above `cnt`
+        // and is never touched.
+        int* seg = r + lo;
+        int npow2 = 64;
+        while (npow2 < cnt) npow2 <<= 1;
+        const int half = npow2 >> 1;
+        for (int k = 2; k <= npow2; k <<= 1) {
+            const int hk = k >> 1;
+            for (int i = lane; i < half; i += 32) {
+                const int blk = i / hk, pos = i - blk * hk;
+                const int a = blk * k + pos, c = blk * k + (k - 1 - pos);
+                if (c < cnt) {
+                    const int va = seg[a], vc = seg[c];
+                    if (va > vc) { seg[a] = vc; seg[c] = va; }
+                }
             }
-            r[p + 1] = v;
+            __syncwarp();
+            for (int jj = k >> 2; jj >= 1; jj >>= 1) {
+                for (int i = lane; i < half; i += 32) {
+                    const int a = 2 * jj * (i / jj) + (i % jj), c = a + jj;
+                    if (c < cnt) {
+                        const int va = seg[a], vc = seg[c];
+                        if (va > vc) { seg[a] = vc; seg[c] = va; }
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
 }

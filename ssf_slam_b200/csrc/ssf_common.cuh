@@ -13,6 +13,17 @@
         if (e__ != cudaSuccess) return ssf_set_error(e__);  \
     } while (0)
 
+// Kernel function attributes (opt-in shared memory above 48 KB) are PER DEVICE: a process that drives several GPUs must set
+// them once on each.  `seen` is a per-call-site bitmask over device ordinals; ssf_attr_needed() is true until ssf_attr_done()
+// has been called on the current device (setting an attribute twice from racing threads is harmless).
+static inline unsigned long long ssf_device_bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+}
+static inline bool ssf_attr_needed(const unsigned long long* seen) { return !(__atomic_load_n(seen, __ATOMIC_ACQUIRE) & ssf_device_bit()); }
+static inline void ssf_attr_done(unsigned long long* seen) { __atomic_fetch_or(seen, ssf_device_bit(), __ATOMIC_RELEASE); }
+
 int ssf_set_error(cudaError_t e);
 int ssf_arg_error(const char* msg);
 void ssf_count_launch();

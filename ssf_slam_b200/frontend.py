@@ -17,6 +17,8 @@ Mirrors, with NumPy arrays in and out exactly like the reference's in-process co
 * ``SceneFlowFrontEnd`` -- network + mask + ego-motion for batches of frame pairs held in HOST memory (the end-to-end
   call ``bench.py`` times: H2D of the clouds, all kernels, D2H of masks and poses).
 """
+import warnings
+
 import numpy as np
 import torch
 
@@ -29,11 +31,25 @@ def _dev(a, dtype, device):
 
 
 def slove_RT_by_SVD(src, dst, device="cuda:0"):
-    """Un-weighted rigid fit dst ~= R @ src + t over all rows; src, dst [M,3] array-likes -> (R [3,3], t [3,1]) float64."""
-    nat.require_device()
-    src_t = torch.from_numpy(np.ascontiguousarray(src, np.float32)).to(device).unsqueeze(0)
-    dst_t = torch.from_numpy(np.ascontiguousarray(dst, np.float32)).to(device).unsqueeze(0)
-    _, _, pose = F_.frontend(dst_t, src_t, mode=2, want_pose=True)
+    """Un-weighted rigid fit dst ~= R @ src + t over all rows; src, dst [M,3] array-likes -> (R [3,3], t [3,1]) float64.
+    Precision follows the input like the reference's numpy code does: float64 clouds are reduced in float64 end to end
+    (`ssf_solve_rt_f64`; R within 1e-9 and t within 1e-6 of the reference), float32 clouds are read as float32 and accumulated in
+    float64.  Fewer than 3 points cannot fix a rotation: the identity is returned with a warning (numpy's SVD would return an
+    arbitrary member of the solution set)."""
+    nat.require_device(device)
+    src, dst = np.asarray(src), np.asarray(dst)
+    if src.shape != dst.shape or src.ndim != 2 or src.shape[1] != 3:
+        raise ValueError("slove_RT_by_SVD: src and dst must both be [M,3]")
+    if src.shape[0] < 3:
+        warnings.warn("slove_RT_by_SVD: fewer than 3 point pairs, returning the identity pose")
+    if src.dtype == np.float32 and dst.dtype == np.float32:
+        src_t = torch.from_numpy(np.ascontiguousarray(src)).to(device).unsqueeze(0)
+        dst_t = torch.from_numpy(np.ascontiguousarray(dst)).to(device).unsqueeze(0)
+        _, _, pose = F_.frontend(dst_t, src_t, mode=2, want_pose=True)
+    else:
+        src_t = torch.from_numpy(np.ascontiguousarray(src, np.float64)).to(device).unsqueeze(0)
+        dst_t = torch.from_numpy(np.ascontiguousarray(dst, np.float64)).to(device).unsqueeze(0)
+        _, pose = F_.solve_rt_f64(src_t, dst_t)
     pose = pose[0].cpu().numpy()
     return pose[:9].reshape(3, 3).copy(), pose[9:].reshape(3, 1).copy()
 
@@ -66,11 +82,14 @@ def odometry(points, flow, mask=None, sem=None, inst=None, movable=(), tau=0.10,
     if single:
         out = {k: v[0] for k, v in out.items()}
         out["bg_index"] = np.flatnonzero(out["mask"] == 0)
+    else:
+        out["bg_index"] = [np.flatnonzero(mk == 0) for mk in out["mask"]]   # ragged: one ascending index array per cloud
     return out
 
 
 def background_index(points, flow, sem=None, inst=None, movable=(), tau=0.10, device="cuda:0"):
-    """bg_index (ascending int64) of the static points, the quantity the drivers feed to slove_RT_by_SVD."""
+    """bg_index (ascending int64) of the static points, the quantity the drivers feed to slove_RT_by_SVD; for batched
+    [B,N,3] input a list of B such arrays."""
     return odometry(points, flow, sem=sem, inst=inst, movable=movable, tau=tau, device=device)["bg_index"]
 
 

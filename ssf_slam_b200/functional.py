@@ -5,6 +5,7 @@ weights are K-major ``[Cin, Cout]`` (see ``ssf_slam_b200.model.prepare_weights``
 launch of ours on the current stream; nothing here computes with torch ops.
 """
 import ctypes
+import threading
 
 import torch
 
@@ -144,23 +145,32 @@ def fps(xyz, npoint):
 # brute-force scan.  Both return identical indices.
 KNN_BLOCKS_MIN_REF = 512
 KNN_BLOCKS_MAX_REF = 16384
-_knn_cache = {}
+_knn_tls = threading.local()   # per-thread: forwards running in different Python threads (or DataParallel replicas) never share it
+
+
+def _knn_cache():
+    c = getattr(_knn_tls, "cache", None)
+    if c is None:
+        c = _knn_tls.cache = {}
+    return c
 
 
 def knn_cache_clear():
-    """Drops the per-cloud search structures (call at the start of every forward: clouds are new tensors each time)."""
-    _knn_cache.clear()
+    """Drops the calling thread's per-cloud search structures (call at the start of every forward: clouds are new tensors each
+    time)."""
+    _knn_cache().clear()
 
 
 def _knn_blocks(ref):
-    key = (ref.data_ptr(), tuple(ref.shape), tuple(ref.stride()))
-    hit = _knn_cache.get(key)
+    key = (ref.device.index, ref.data_ptr(), tuple(ref.shape), tuple(ref.stride()))
+    _knn_cache_ = _knn_cache()
+    hit = _knn_cache_.get(key)
     if hit is None:
         B, Nr, _ = ref.shape
         ws = torch.empty(int(nat.lib().ssf_knn_blocks_workspace_floats(B, Nr)), dtype=torch.float32, device=ref.device)
         nat.check(nat.lib().ssf_knn_blocks_build(nat.ptr(ref), B, Nr, nat.ptr(ws), nat.stream()))
         hit = (ref, ws)  # keeping `ref` alive pins its storage, so the pointer in the key cannot be recycled
-        _knn_cache[key] = hit
+        _knn_cache_[key] = hit
     return hit[1]
 
 
@@ -252,12 +262,22 @@ def frontend(points, flow, mode=1, in_mask=None, sem=None, movable=(), inst=None
     pose = torch.empty(B, 12, dtype=torch.float64, device=dev) if want_pose else None
     bits = 0
     for c in movable:
-        if 0 <= int(c) < 64:
-            bits |= 1 << int(c)
+        if not 0 <= int(c) < 64:
+            raise nat.SsfError("movable class ids must lie in [0, 64) (they are passed to the kernel as a 64-bit set); got %d" % int(c))
+        bits |= 1 << int(c)
     nat.check(nat.lib().ssf_frontend(nat.ptr(points), nat.ptr(flow), B, N, mode, nat.ptr(in_mask), nat.ptr(sem), bits,
                                      nat.ptr(inst), int(n_inst), float(tau), nat.ptr(mask), nat.ptr(odom), nat.ptr(pose),
                                      nat.stream()))
     return (mask, odom, pose) if want_pose else (mask, odom)
+
+
+def solve_rt_f64(src, dst):
+    """src, dst f64 [B,M,3] -> (odom f64 [B,7], pose f64 [B,12]): dst ~= R src + t, reduced in float64."""
+    B, M, _ = src.shape
+    odom = torch.empty(B, 7, dtype=torch.float64, device=src.device)
+    pose = torch.empty(B, 12, dtype=torch.float64, device=src.device)
+    nat.check(nat.lib().ssf_solve_rt_f64(nat.ptr(src), nat.ptr(dst), B, M, nat.ptr(odom), nat.ptr(pose), nat.stream()))
+    return odom, pose
 
 
 def gmm_mask(points, flow, max_iter=100, tol=1e-3, want_info=False):

@@ -45,6 +45,16 @@ class _OwnWeights:
         object.__setattr__(self, "_own_cache", None)
         return super()._load_from_state_dict(*args, **kwargs)
 
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        return super().load_state_dict(_strip_module_prefix(state_dict), strict=strict, **kw)
+
+
+def _strip_module_prefix(state_dict):
+    """nn.DataParallel checkpoints: drop a leading ``module.`` when every key carries it."""
+    if len(state_dict) and all(k.startswith("module.") for k in state_dict):
+        return type(state_dict)((k[7:], v) for k, v in state_dict.items())
+    return state_dict
+
 
 def _pm(x):
     """reference layout [B,C,N] -> point-major [B,N,C] (contiguous fp32)"""
@@ -522,8 +532,10 @@ class TFlow(nn.Module):
         return super()._load_from_state_dict(*args, **kwargs)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts the reference's checkpoints as they are saved: plain keys, or every key under nn.DataParallel's ``module.``
+        prefix (the reference driver builds such dicts, ASF/main_sju_occ_ros.py:706-709)."""
         self._prepared = None
-        return super().load_state_dict(state_dict, strict=strict, **kw)
+        return super().load_state_dict(_strip_module_prefix(state_dict), strict=strict, **kw)
 
     def weights(self, device):
         if self._prepared is None or self._prepared[0] != device:

@@ -96,12 +96,37 @@ def _scan(scene, f, rng):
     inst = np.zeros(nr, np.int32)
     veh = np.full(nr, -1, np.int32)
 
-    def take(th, s, i, v):
-        m = th < best
-        best[m] = th[m]
-        sem[m] = s
-        inst[m] = i
-        veh[m] = v
+    def take(th, s, i, v, rows=None):
+        if rows is None:
+            m = th < best
+            best[m] = th[m]
+            sem[m] = s
+            inst[m] = i
+            veh[m] = v
+        else:   # th holds the rays `rows` only
+            m = th < best[rows]
+            r = rows[m]
+            best[r] = th[m]
+            sem[r] = s
+            inst[r] = i
+            veh[r] = v
+
+    az = np.arctan2(d[:, 1], d[:, 0])
+
+    def rays_towards(corners_xy):
+        """Indices of the rays whose azimuth lies inside the angle the footprint subtends (plus a margin); None = all rays
+        (sensor inside or next to the footprint).  Small objects are hit by a few percent of the 65536 rays, so only those
+        are intersected."""
+        rel = corners_xy - t[:2]
+        if np.min(np.hypot(rel[:, 0], rel[:, 1])) < 0.5 or (rel[:, 0].min() < 0 < rel[:, 0].max() and rel[:, 1].min() < 0 < rel[:, 1].max()):
+            return None
+        ang = np.arctan2(rel[:, 1], rel[:, 0])
+        c = np.arctan2(rel[:, 1].mean(), rel[:, 0].mean())
+        dif = (ang - c + np.pi) % (2 * np.pi) - np.pi
+        if dif.max() - dif.min() > np.pi / 2:
+            return None
+        da = (az - c + np.pi) % (2 * np.pi) - np.pi
+        return np.flatnonzero((da >= dif.min() - 0.02) & (da <= dif.max() + 0.02))
 
     # ground (z = 0): blocks rays, later dropped ("rm_road")
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -111,16 +136,24 @@ def _scan(scene, f, rng):
         y = sgn * scene.half_width
         take(_slab(o, d, np.array([-100.0, min(y, y + sgn), 0.0]), np.array([400.0, max(y, y + sgn), scene.wall_h])),
              SEM_BUILDING, 0, -1)
+    sq = np.array([[-1.0, -1.0], [-1.0, 1.0], [1.0, -1.0], [1.0, 1.0]])
     for (px, py, ph) in scene.poles:
-        take(_slab(o, d, np.array([px - 0.15, py - 0.15, 0.0]), np.array([px + 0.15, py + 0.15, ph])), SEM_POLE, 0, -1)
+        rows = rays_towards(np.array([px, py]) + 0.15 * sq)
+        lo, hi = np.array([px - 0.15, py - 0.15, 0.0]), np.array([px + 0.15, py + 0.15, ph])
+        if rows is None:
+            take(_slab(o, d, lo, hi), SEM_POLE, 0, -1)
+        elif len(rows):
+            take(_slab(o[rows], d[rows], lo, hi), SEM_POLE, 0, -1, rows)
     vxy = scene.veh_pose(f)
     half = scene.veh_size / 2
     for k in range(len(vxy)):
         Rv = _rot_z(scene.veh_yaw[k])
         c = np.array([vxy[k, 0], vxy[k, 1], half[2]])
-        ol = (o - c) @ Rv
-        dl = d @ Rv
-        take(_slab(ol, dl, -half, half), SEM_VEHICLE, k + 1, k)
+        rows = rays_towards(vxy[k] + (sq * half[:2]) @ Rv[:2, :2].T)
+        if rows is None:
+            take(_slab((o - c) @ Rv, d @ Rv, -half, half), SEM_VEHICLE, k + 1, k)
+        elif len(rows):
+            take(_slab((o[rows] - c) @ Rv, d[rows] @ Rv, -half, half), SEM_VEHICLE, k + 1, k, rows)
     ok = np.isfinite(best) & (best <= 100.0) & (sem >= 0)
     noise = 0.01 * rng.standard_normal(nr)
     pts = _DIRS[ok] * (best[ok] + noise[ok])[:, None]

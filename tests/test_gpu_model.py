@@ -59,6 +59,128 @@ def test_set_abstraction_teacher_forced(setup, lvl):
     assert err < 2e-5 * max(1.0, float(inter["f1"][lvl].abs().max())), err
 
 
+@pytest.fixture(scope="module")
+def setup8k(golden_dir, oracle_c):
+    """The N = 8192 golden pair (BASELINE configs 1/2/4 size) with every intermediate of the oracle port, so that each fused
+    layer -- including the tcgen05 m = 64 cost volume of levels 1 and 0, the dominant kernel -- is fed exactly what the
+    reference fed its own layer (identical neighbour sets) and compared output by output."""
+    from ssf_slam_b200.model import prepare_weights
+    g = np.load(os.path.join(golden_dir, "tflow_n8192.npz"))
+    sd = tp.random_init_state_dict(int(g["weight_seed"]))
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0)
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0)
+    (flows, fps), inter = tp.tflow_forward(sd, pc1, pc2, return_intermediates=True)
+    for i in range(4):   # the port at this size is the golden (written by the unmodified reference), bit for bit
+        assert np.array_equal(flows[i][0].numpy(), g["flow%d" % i])
+    return dict(sd=sd, inter=inter, W=prepare_weights(sd, torch.device("cuda:0")))
+
+
+@pytest.mark.parametrize("lvl", [2, 1, 0])
+def test_set_upconv_teacher_forced_n8192(setup8k, lvl):
+    """a5: su2 / su1 / su0 (both clouds) against the oracle port's own outputs at N = 8192."""
+    from ssf_slam_b200.model import set_upconv_pm
+    inter = setup8k["inter"]
+    io = inter["in%d" % lvl]
+    for pcs, f, prev, want in ((inter["pcs1"], inter["f1"], io["prev1"], io["u1"]), (inter["pcs2"], inter["f2"], io["prev2"], io["u2"])):
+        got = set_upconv_pm(setup8k["W"][io["su"]], 16, _pm(pcs[lvl]), _pm(pcs[lvl + 1]), _pm(f[lvl]), _pm(prev))
+        err = float((_cm(got) - want).abs().max())
+        assert err < 2e-5 * max(1.0, float(want.abs().max())), (lvl, err)
+
+
+@pytest.mark.parametrize("lvl", [2, 1, 0])
+def test_cost_volume_teacher_forced_n8192(setup8k, lvl):
+    """a6: flow2_r (un-fused tcgen05 path, m = 128) and flow1_r / flow0_r (the fused tcgen05 kernel `cost_volume_tc64`, m = 64)
+    against the oracle port at N = 8192: warp, both kNNs, both branches, attention, weightnet, forward / backward cost, flow head."""
+    from ssf_slam_b200.model import cost_volume_pm, point_warping_pm
+    inter = setup8k["inter"]
+    io = inter["in%d" % lvl]
+    p1, p2 = inter["pcs1"][lvl], inter["pcs2"][lvl]
+    want_warp = tp.point_warping(p1, p2, io["coarse"], io["k_warp"])
+    warped = point_warping_pm(_pm(p1), _pm(p2), _pm(io["coarse"]), io["k_warp"])
+    assert float((_cm(warped) - want_warp).abs().max()) < 1e-5
+    got = cost_volume_pm(setup8k["W"][io["fr"]], _pm(p1), _pm(p2), _pm(want_warp), _pm(io["u1"]), _pm(io["cfu"]), _pm(io["u2"]),
+                         _pm(io["cbu"]), sf=_pm(io["coarse"]), sf_feat=_pm(io["sf_feat"]))
+    want = inter["l%d" % lvl]
+    for n, w_, g_ in zip(("cost_fwd", "cost_bwd", "feats", "flow"), want, got):
+        w_ = w_ if n != "cost_bwd" else torch.nn.functional.pad(w_, (0, g_.shape[1] - w_.shape[2]))
+        err = float((_cm(g_) - w_).abs().max())
+        assert err < 3e-5 * max(1.0, float(w_.abs().max())), (lvl, n, err)
+
+
+def test_cost_volume_tc64_kernel_vs_oracle_internals(setup8k):
+    """The fused tcgen05 kernel's raw outputs at level 0 (N1 = 8192, m = 64) against the oracle port's internals: the forward
+    cost, and the warped-branch logits gw and rows Cw that feed the segmented softmax (soflow.py:397-469)."""
+    from ssf_slam_b200 import functional as F_
+    inter, sd, W = setup8k["inter"], setup8k["sd"], setup8k["W"]["flow0_r"]
+    io = inter["in0"]
+    p1, p2 = inter["pcs1"][0], inter["pcs2"][0]
+    warp = tp.point_warping(p1, p2, io["coarse"], io["k_warp"])
+    _, aux = tp.cost_volume(sd, "flow0_r.cost", 16, True, p1, p2, warp, torch.cat([io["u1"], io["cfu"]], 1),
+                            torch.cat([io["u2"], io["cbu"]], 1), io["coarse"], io["sf_feat"], return_aux=True)
+    m = 64
+    idx, idxw = aux["idx"].int().cuda().contiguous(), aux["idxw"].int().cuda().contiguous()
+    Hab = F_.dense_tc(W["Hab_img"], 2 * m, W["D"], x1=_pm(io["u1"]), x2=_pm(io["cfu"]), bias=W["bab"])
+    Gab = F_.dense_tc(W["Gab_img"], 2 * m, W["D"], x1=_pm(io["u2"]), x2=_pm(io["cbu"]))
+    H3 = F_.dense_tc(W["H3_img"], m, W["F"], x1=_pm(io["sf_feat"]), bias=W["b3"])
+    cost_fwd, cost_fwd_cm, gw, Cw = F_.cost_volume(Gab, Hab, W, H3, _pm(p1), _pm(p2), idx, idxw, m)
+    want_fwd = inter["l0"][0]                                                     # [1, m, N1]
+    assert float((cost_fwd_cm.cpu() - want_fwd).abs().max()) < 3e-5 * max(1.0, float(want_fwd.abs().max()))
+    assert torch.equal(cost_fwd.permute(0, 2, 1).contiguous(), cost_fwd_cm)
+    want_gw = aux["gw"].permute(0, 3, 2, 1).reshape(1, -1)                        # [1, N1*16]
+    want_cw = aux["cw"].permute(0, 3, 2, 1).reshape(1, -1, m)
+    assert float((gw.cpu() - want_gw).abs().max()) < 3e-5 * max(1.0, float(want_gw.abs().max()))
+    assert float((Cw.cpu() - want_cw).abs().max()) < 3e-5 * max(1.0, float(want_cw.abs().max()))
+
+
+class _CudaOps:
+    """`ops` namespace for oracle/tflow_port.py whose point operators are the CUDA drop-ins behind the B-op boundary
+    (ssf_slam_b200.pointnet2_utils / scatter, called with the reference's argument layouts); CPU tensors in and out."""
+
+    def __init__(self):
+        from ssf_slam_b200 import pointnet2_utils as pu, scatter
+        self.pu, self.sc = pu, scatter
+
+    def _c(self, t):
+        return t.contiguous().cuda()
+
+    def furthest_point_sample(self, xyz, n):
+        return self.pu.furthest_point_sample(self._c(xyz), n).cpu()
+
+    def gather_operation(self, f, idx):
+        return self.pu.gather_operation(self._c(f), self._c(idx.int())).cpu()
+
+    def knn(self, k, q, r):
+        d, i = self.pu.knn(k, self._c(q), self._c(r))
+        return d.cpu(), i.cpu()
+
+    def three_nn(self, q, r):
+        d, i = self.pu.three_nn(self._c(q), self._c(r))
+        return d.cpu(), i.cpu()
+
+    def grouping_operation(self, f, idx):
+        return self.pu.grouping_operation(self._c(f.float()), self._c(idx.int())).cpu()
+
+    def scatter_softmax(self, src, index, dim=1):
+        return self.sc.scatter_softmax(self._c(src), self._c(index), dim=dim).cpu()
+
+    def scatter_sum(self, src, index, dim=1, dim_size=None):
+        return self.sc.scatter_sum(self._c(src), self._c(index), dim=dim, dim_size=dim_size).cpu()
+
+
+def test_reference_side_code_through_the_bop_boundary(setup, monkeypatch):
+    """B-op: the reference-side model code (the oracle port = the reference's torch layers, pinned bit-exact to the unmodified
+    reference) run with the CUDA drop-ins as its `lib.pointnet2_utils` / `torch_scatter` -- the integration INTEGRATION.md
+    describes, on the GPU box.  FPS indices equal the reference golden; flows within the north-star tolerance (only the scatter's summation order and expf differ)."""
+    g = setup["g"]
+    monkeypatch.setattr(tp, "ops", _CudaOps())
+    flows, fps = tp.tflow_forward(setup["sd"], setup["pc1"], setup["pc2"])
+    for i in range(3):
+        assert np.array_equal(fps[i][0].numpy(), g["fps%d" % (i + 1)])
+    errs = [float(np.abs(flows[i][0].numpy() - g["flow%d" % i]).max()) for i in range(4)]
+    print("port over CUDA B-ops vs reference golden, flow max-abs error per level:", errs)
+    assert max(errs) <= FLOW_TOL, errs
+
+
 @pytest.mark.parametrize("lvl,name", [(3, "su3")])
 def test_set_upconv_teacher_forced(setup, lvl, name):
     from ssf_slam_b200.model import set_upconv_pm
@@ -174,25 +296,38 @@ def test_frontend_pipeline_host_buffers(setup, golden_dir):
     assert np.array_equal(out["odom"][0].numpy(), want["odom"])
 
 
-def test_tflow_n16384_tensor_core_vs_simt_path(setup):
-    """BASELINE config 3 size (N = 16384, no oracle golden at this size): the tensor-core realisation and the SIMT fp32
-    realisation of the dense layers must give the same FPS indices and flows within the north-star tolerance."""
+def test_tflow_n16384_vs_reference_golden_and_seg_masker(setup, golden_dir):
+    """BASELINE config 3 (Seg pipeline, N = 16384): golden written by the unmodified reference TFlow at N = 16384
+    (oracle/gen_golden.py): FPS exact, flows <= 1e-4; then the Seg masker (semantic seed + per-instance voting) and the pose on
+    the GPU's own flow, bit-exact against the specification.  The SIMT realisation must agree with the tensor-core one too."""
+    from oracle import frontend as ofe
     from ssf_slam_b200 import functional as F_, synth
-    it = synth.make_sequence(2000, 1, 16384)[0]
-    pc1 = torch.from_numpy(it["pos1"].T.copy()).unsqueeze(0).cuda()
-    pc2 = torch.from_numpy(it["pos2"].T.copy()).unsqueeze(0).cuda()
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    g = np.load(os.path.join(golden_dir, "tflow_n16384.npz"))
     net = setup["net"]
+    pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0).cuda()
+    pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0).cuda()
     flows_tc, fps_tc = net(pc1, pc2)
+    for i in range(3):
+        assert np.array_equal(fps_tc[i][0].cpu().numpy(), g["fps%d" % (i + 1)]), "fps level %d" % (i + 1)
+    errs = [float(np.abs(flows_tc[i][0].cpu().numpy() - g["flow%d" % i]).max()) for i in range(4)]
+    print("N=16384 flow max-abs error per level vs the reference golden:", errs)
+    assert flows_tc[0].shape == (1, 3, 16384) and max(errs) <= FLOW_TOL
     F_.USE_TC = False
     try:
-        flows_ref, fps_ref = net(pc1, pc2)
+        flows_simt, fps_simt = net(pc1, pc2)
     finally:
         F_.USE_TC = True
-    for a, b in zip(fps_tc, fps_ref):
+    for a, b in zip(fps_tc, fps_simt):
         assert torch.equal(a, b)
-    errs = [float((a - b).abs().max()) for a, b in zip(flows_tc, flows_ref)]
-    print("N=16384 tensor-core vs SIMT flow max-abs diff per level:", errs)
-    assert flows_tc[0].shape == (1, 3, 16384) and max(errs) <= FLOW_TOL
+    assert max(float(np.abs(flows_simt[i][0].cpu().numpy() - g["flow%d" % i]).max()) for i in range(4)) <= FLOW_TOL
+    fe = SceneFlowFrontEnd(net, tau=0.10, movable=synth.MOVABLE_CLASSES)
+    n_inst = int(g["inst"].max()) + 1
+    out = fe.process(g["pos1"][None], g["pos2"][None], sem=g["sem"][None], inst=g["inst"][None], n_inst=n_inst, return_flow=True)
+    flow = out["flow"][0].numpy()
+    want = ofe.masker_spec(g["pos1"], flow, 0.10, sem=g["sem"], inst=g["inst"], movable=synth.MOVABLE_CLASSES)
+    assert np.array_equal(out["mask"][0].numpy(), want["mask"])
+    assert np.array_equal(out["odom"][0].numpy(), want["odom"])
 
 
 def test_frontend_cuda_graph_replay_equals_eager(setup, golden_dir):

@@ -44,6 +44,25 @@ def test_golden_point_ops(pu, golden_dir):
         assert np.array_equal(bc.cpu().numpy(), g["ball_r%g_cnt" % r])
 
 
+def test_reference_twins_golden(pu, golden_dir):
+    """a10 pin on the GPU: the CUDA operators against outputs of the reference's OWN in-tree pure-torch twins of the
+    extension (ASF/utils/utils.py:68-108, ASF/SetCover.py:39-63; written by oracle/gen_golden_point_twins.py from the
+    unmodified reference source on tie-free clouds)."""
+    g = np.load(os.path.join(golden_dir, "point_twins.npz"))
+    assert np.array_equal(pu.furthest_point_sample(_cuda(g["fps_xyz"]), 512).cpu().numpy(), g["fps_idx"])
+    q, r = _cuda(g["knn_query"]), _cuda(g["knn_ref"])
+    for k in (3, 8, 16):
+        d, i = pu.knn(k, q, r)
+        assert np.array_equal(i.cpu().numpy(), g["knn%d_idx" % k])
+        assert np.allclose(d.cpu().numpy(), g["knn%d_dist" % k], rtol=1e-5, atol=1e-6)
+    d, i = pu.three_nn(q, r)
+    assert np.array_equal(i.cpu().numpy(), g["knn3_idx"])
+    for rad in (0.5, 1.0, 2.0, 4.0):
+        bi, bc = pu.ball_query(rad, 16, _cuda(g["ball_xyz"]), _cuda(g["ball_new_xyz"]), return_count=True)
+        assert np.array_equal(bi.cpu().numpy(), g["ball_r%g_idx" % rad])
+        assert np.array_equal(bc.cpu().numpy(), g["ball_r%g_cnt" % rad])
+
+
 @pytest.mark.parametrize("N,npoint", [(8192, 2048), (2048, 512), (512, 256), (256, 128), (100, 37), (1, 1), (5000, 300),
                                       (130, 140), (16384, 1024), (20000, 512), (65536, 2048)])
 def test_fps(pu, N, npoint):
@@ -217,6 +236,28 @@ def test_knn_warp_scan_large_cloud_few_queries(pu, B, Nq, Nr, k):
     off = (np.random.default_rng(4).standard_normal(q.shape) * 0.3).astype(np.float32)
     _, i2 = pu.knn(k, _cuda(q), _cuda(ref), offset=_cuda(off))
     assert np.array_equal(i2.cpu().numpy(), po.c_knn(k, q + off, ref)[1])
+
+
+def test_config5_dense_stress_n65536(pu):
+    """BASELINE config 5 (N = 65536 per cloud): the full 65536 x 65536 k = 16 search (every query; the oracle checks a strided
+    query subsample and all rows that sit on duplicated points), FPS 65536 -> 2048, and the ball-query radius sweep
+    0.5 / 1 / 2 / 4 m around the FPS centres, against the plain-C oracle; lidar-like anisotropic cloud with exact duplicates."""
+    N = 65536
+    rng = np.random.default_rng(65536)
+    xyz = (rng.standard_normal((1, N, 3)) * np.array([30.0, 20.0, 2.0])).astype(np.float32)
+    xyz[:, N // 2:N // 2 + 2048] = xyz[:, :2048]          # exact duplicates -> exact ties
+    x = _cuda(xyz)
+    d, i = pu.knn(16, x, x)
+    rows = np.unique(np.concatenate([np.arange(0, N, 97), np.arange(0, 256), np.arange(N // 2, N // 2 + 256)]))
+    od, oi = po.c_knn(16, xyz[:, rows], xyz)
+    assert np.array_equal(i.cpu().numpy()[:, rows], oi) and np.array_equal(d.cpu().numpy()[:, rows], od)
+    fps = pu.furthest_point_sample(x, 2048)
+    assert np.array_equal(fps.cpu().numpy(), po.c_fps(xyz, 2048))
+    cent = np.ascontiguousarray(xyz[0][fps.cpu().numpy()[0].astype(np.int64)][None])
+    for r in (0.5, 1.0, 2.0, 4.0):
+        bi, bc = pu.ball_query(r, 16, x, _cuda(cent), return_count=True)
+        oi, oc = po.c_ball_query(r, 16, xyz, cent)
+        assert np.array_equal(bc.cpu().numpy(), oc) and np.array_equal(bi.cpu().numpy(), oi), r
 
 
 def test_error_behaviour_python_exceptions(pu):

@@ -16,7 +16,7 @@ def _run(K, N, mode, passes, seed=0):
     hi, lo = tc.weight_image(W)
     Y = torch.full((128, N), float("nan"), device="cuda")
     Xd, hid, lod = X.cuda(), hi.cuda(), lo.cuda()  # keep the device tensors alive across the launch
-    nat.check(nat.lib().ssf_tc_gemm_test(nat.ptr(Xd), nat.ptr(hid), nat.ptr(lod), K, N, mode, passes, nat.ptr(Y), nat.stream()))
+    nat.check(nat.dev_lib().ssf_tc_gemm_test(nat.ptr(Xd), nat.ptr(hid), nat.ptr(lod), K, N, mode, passes, nat.ptr(Y), nat.stream()), nat.dev_lib())
     torch.cuda.synchronize()
     ref = (X.double() @ W.double().t())
     err = float((Y.cpu().double() - ref).abs().max())

@@ -22,6 +22,22 @@ def test_state_dict_surface_matches_reference_format():
         assert tuple(v.shape) == tuple(sd[k].shape), k
 
 
+def test_strict_load_of_dataparallel_checkpoint():
+    """The reference saves / builds `module.`-prefixed dicts (ASF/main_sju_occ_ros.py:706-709): strict load must take them."""
+    from ssf_slam_b200 import model as M
+    from ssf_slam_b200.weights import random_init_state_dict
+    sd = random_init_state_dict(1)
+    net = M.TFlow()
+    res = net.load_state_dict({"module." + k: v for k, v in sd.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    sa = M.PointNetSetAbstraction(512, 2.0, 16, 64, [64, 64, 128])
+    sa.load_state_dict({"module." + k[4:]: v for k, v in sd.items() if k.startswith("sa2.")}, strict=True)
+    with pytest.raises(RuntimeError):
+        net.load_state_dict({"module." + k: v for k, v in list(sd.items())[:-1]}, strict=True)   # a missing key still raises
+
+
 def test_bn_folding_equals_conv_bn_eval():
     from ssf_slam_b200.model import prepare_weights
     from ssf_slam_b200.weights import random_init_state_dict
@@ -71,9 +87,15 @@ def _gloo_worker(rank, world, port, q):
     from ssf_slam_b200.shard import gather_results, my_sequences
     dist.init_process_group("gloo", rank=rank, world_size=world)
     seqs = my_sequences(64, rank, world)
-    odom = torch.full((2, 3, 7), float(rank), dtype=torch.float64)
+    odom = torch.full((2, 3, 7), float(rank), dtype=torch.float64) + torch.arange(7, dtype=torch.float64) / 8
     mask = torch.full((2, 3, 16), rank, dtype=torch.uint8)
-    od, mk = gather_results(odom, mask)
+    mask[..., 5] = 200 + rank
+    od, mk = gather_results(odom, mask)      # one packed all_gather_into_tensor
+    ok = od.shape == (world, 2, 3, 7) and mk.shape == (world, 2, 3, 16) and od.dtype == torch.float64
+    for r in range(world):
+        ok = ok and bool((od[r] == float(r) + torch.arange(7, dtype=torch.float64) / 8).all())
+        ok = ok and bool((mk[r][..., 5] == 200 + r).all()) and bool((mk[r][..., 0] == r).all())
+    assert ok
     q.put((rank, seqs, od[:, 0, 0, 0].tolist(), mk[:, 0, 0, 0].tolist()))
     dist.destroy_process_group()
 

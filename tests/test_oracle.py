@@ -27,6 +27,26 @@ def test_point_ops_c_and_torch_match_golden(golden_dir, oracle_c):
         assert np.array_equal(ti.numpy(), bi) and np.array_equal(tc.numpy(), bc)
 
 
+def test_point_ops_match_reference_twins_golden(golden_dir, oracle_c):
+    """a10 pin: tests/golden/point_twins.npz holds the outputs of the reference's own pure-torch twins of the extension
+    (farthest_point_sample / knn_point, ASF/utils/utils.py:68-108; query_ball_point, ASF/SetCover.py:39-63), executed
+    unmodified by oracle/gen_golden_point_twins.py on tie-free clouds.  Both oracle restatements must reproduce them."""
+    g = np.load(os.path.join(golden_dir, "point_twins.npz"))
+    assert np.array_equal(point_ops.c_fps(g["fps_xyz"], 512), g["fps_idx"])
+    assert np.array_equal(point_ops.furthest_point_sample_torch(torch.from_numpy(g["fps_xyz"]), 512).numpy(), g["fps_idx"])
+    q, r = g["knn_query"], g["knn_ref"]
+    for k in (3, 8, 16):
+        d, i = point_ops.c_knn(k, q, r)
+        assert np.array_equal(i, g["knn%d_idx" % k]) and np.allclose(d, g["knn%d_dist" % k], rtol=1e-5, atol=1e-6)
+        d2, i2 = point_ops.knn_torch(k, torch.from_numpy(q), torch.from_numpy(r))
+        assert np.array_equal(i2.numpy(), g["knn%d_idx" % k])
+    for rad in (0.5, 1.0, 2.0, 4.0):
+        bi, bc = point_ops.c_ball_query(rad, 16, g["ball_xyz"], g["ball_new_xyz"])
+        assert np.array_equal(bi, g["ball_r%g_idx" % rad]) and np.array_equal(bc, g["ball_r%g_cnt" % rad])
+        ti, tc = point_ops.ball_query(rad, 16, torch.from_numpy(g["ball_xyz"]), torch.from_numpy(g["ball_new_xyz"]))
+        assert np.array_equal(ti.numpy(), bi) and np.array_equal(tc.numpy(), bc)
+
+
 def test_knn_tie_break_lowest_index():
     xyz = np.zeros((1, 40, 3), np.float32)  # every distance ties
     d, i = point_ops.knn_torch(5, torch.zeros(1, 3, 3), torch.from_numpy(xyz))

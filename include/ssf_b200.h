@@ -172,6 +172,16 @@ int ssf_solve_rt_f64(const double* src, const double* dst, int B, int M, double*
 int ssf_gmm_mask(const float* points, const float* flow, int B, int N, int max_iter, double tol, unsigned char* mask_out,
                  double* info_out, void* stream);
 
+/* ---- before the path: the CARLA frame subsampler's data movement on the device, ASF/utils/datasets/carla.py:179-305.
+ * Clouds are index lists into the raw frame.  select: entries of `pre` (NULL = 0..n-1) that pass the ground cut (keep unless
+ * pts[src, ld-1] < ground_z; carla.py:237) and the mask test (mask_mode 0 none, 1 mask != 0, 2 mask == 0, 3 mask == 1; mask u8 indexed
+ * by raw index), in order -> sel (raw indices, capacity n) and *count.  index_compose: out[j] = sel[ind[j]] (sel NULL = identity),
+ * *err set to 1 if an index is outside [0, n_sel).  gather_u8: out[j] = src[idx[j]]. */
+int ssf_dataset_select(const float* pts, int ld, const unsigned char* mask, const int* pre, int n, int ground_cut, float ground_z,
+                       int mask_mode, int* sel, int* count, void* stream);
+int ssf_index_compose(const int* sel, int n_sel, const int* ind, int m, int* out, int* err, void* stream);
+int ssf_gather_u8(const unsigned char* src, int n, const int* idx, int m, unsigned char* out, void* stream);
+
 /* ---- next after the path: plane-feature extraction of the back end's first node, src/frameFeature.cpp:45-127
  * (scan-line id from elevation, stable regrouping per line, 11-tap curvature, greedy selection curvature < plane_min with a
  * skip of plane_span).  points [B,N,3] -> out [B,N,4] = (x, y, z, intensity = indexInRow + line/100), out_count [B].

@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE (oracle): plane-feature extraction of src/frameFeature.cpp:45-127.
 
 Two independent restatements that must agree: ``plane_features_c`` (oracle/c/ssf_oracle.c, line-by-line C) and
-``plane_features_py`` (plain Python/NumPy fp32 loops, small inputs only).  Parity unpinned: the reference node needs
-ROS / PCL and cannot be compiled or run here, and the reference holds no test vectors for it."""
+``plane_features_py`` (plain Python/NumPy fp32 loops, small inputs only).  PINNED against the reference's own node: its
+src/frameFeature.cpp compiles unmodified, from where it lies, against stand-in ROS / PCL headers (oracle/ref_build/ ->
+oracle/_ref/libframe_feature_ref.so); oracle/gen_golden_plane_features.py asserts both restatements equal what that node
+publishes, bit for bit, and commits the vectors (tests/golden/plane_features_ref.npz)."""
 import ctypes
 import math
 import os

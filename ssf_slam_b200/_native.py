@@ -57,6 +57,9 @@ SIGNATURES = {
     "ssf_frontend": ("ppiiippQpifpppp", _I),
     "ssf_solve_rt_f64": ("ppiippp", _I),
     "ssf_gmm_mask": ("ppiiidppp", _I),
+    "ssf_dataset_select": ("pippiifippp", _I),
+    "ssf_index_compose": ("pipippp", _I),
+    "ssf_gather_u8": ("pipipp", _I),
     "ssf_plane_features_workspace_bytes": ("ii", _I64),
     "ssf_plane_features": ("piiiiifipppp", _I),
 }

@@ -10,6 +10,11 @@ The C++ back end pairs message k on ``frame_odom1`` with the k-th plane cloud pu
 * ``frame_odom1`` -- ``std_msgs/Float64MultiArray``: ``data = [tx,ty,tz,qx,qy,qz,qw]``
   (``scripts/PointCloudOdometry.py:97-103``; consumed at ``src/lidarOdometry.cpp:148-154`` as t then Quaterniond(x,y,z,w)).
 
+``serialize_pointcloud2`` / ``serialize_float64_multiarray`` are the full ROS1 (genpy, little-endian) wire serialisations of
+the two messages -- the bytes a subscriber's ``deserialize`` sees on the TCPROS connection after the 4-byte length prefix --
+written from the message definitions (``sensor_msgs/PointCloud2.msg``, ``std_msgs/Header.msg``, ``sensor_msgs/PointField.msg``,
+``std_msgs/Float64MultiArray.msg``, ``std_msgs/MultiArrayLayout.msg``); ``deserialize_*`` are their inverses.  ROS itself is not
+in this image, so the byte goldens in tests/test_host.py are derived by hand from those definitions.
 ``fill_ros_messages`` populates real rospy message objects when ROS is installed (not testable in this image);
 ``integrate_odometry`` replays the back end's pose integration (``src/lidarOdometry.cpp:80-81``) to emit TUM lines.
 """
@@ -46,6 +51,93 @@ def serialize_float64_multiarray(odom7):
     uint32 dim count (0), uint32 data_offset (0), uint32 data length, then the float64s."""
     o = np.asarray(odom7, np.float64).reshape(-1)
     return struct.pack("<III", 0, 0, len(o)) + o.astype("<f8").tobytes()
+
+
+def _ros_string(text):
+    b = text.encode("utf-8")
+    return struct.pack("<I", len(b)) + b
+
+
+def serialize_pointcloud2(points, seq=0, stamp=(0, 0), declare_intensity=False, frame_id="livox_frame"):
+    """Full ROS1 wire bytes of the ``velodyne_points`` message for points [N,3] (fields, steps and flags as the reference
+    drivers set them).  Layout, all little endian:
+      Header   : uint32 seq | uint32 stamp.secs | uint32 stamp.nsecs | uint32 len + frame_id
+      uint32 height | uint32 width
+      fields[] : uint32 count, then per field: uint32 len + name | uint32 offset | uint8 datatype | uint32 count
+      uint8 is_bigendian | uint32 point_step | uint32 row_step | uint32 len + data | uint8 is_dense"""
+    d = pointcloud2_dict(points, declare_intensity, frame_id)
+    return serialize_pointcloud2_dict(d, seq, stamp)
+
+
+def serialize_pointcloud2_dict(d, seq=0, stamp=(0, 0)):
+    out = [struct.pack("<III", seq, int(stamp[0]), int(stamp[1])), _ros_string(d["frame_id"]),
+           struct.pack("<II", d["height"], d["width"]), struct.pack("<I", len(d["fields"]))]
+    for name, offset, datatype, count in d["fields"]:
+        out += [_ros_string(name), struct.pack("<IBI", offset, datatype, count)]
+    out += [struct.pack("<BII", 1 if d["is_bigendian"] else 0, d["point_step"], d["row_step"]),
+            struct.pack("<I", len(d["data"])), bytes(d["data"]), struct.pack("<B", 1 if d["is_dense"] else 0)]
+    return b"".join(out)
+
+
+def deserialize_pointcloud2(buf):
+    """Inverse of serialize_pointcloud2 -> dict(seq, stamp, frame_id, height, width, fields, is_bigendian, point_step,
+    row_step, data, is_dense); raises ValueError on trailing or missing bytes."""
+    pos = 0
+
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from(fmt, buf, pos)
+        pos += struct.calcsize(fmt)
+        return v
+
+    def string():
+        nonlocal pos
+        (n,) = take("<I")
+        v = bytes(buf[pos:pos + n])
+        if len(v) != n:
+            raise ValueError("truncated message")
+        pos += n
+        return v
+
+    try:
+        seq, secs, nsecs = take("<III")
+        frame_id = string().decode("utf-8")
+        height, width = take("<II")
+        (nf,) = take("<I")
+        fields = []
+        for _ in range(nf):
+            name = string().decode("utf-8")
+            offset, datatype, count = take("<IBI")
+            fields.append((name, offset, datatype, count))
+        big, point_step, row_step = take("<BII")
+        data = string()
+        (dense,) = take("<B")
+    except struct.error as e:
+        raise ValueError("truncated message") from e
+    if pos != len(buf):
+        raise ValueError("%d trailing bytes" % (len(buf) - pos))
+    return dict(seq=seq, stamp=(secs, nsecs), frame_id=frame_id, height=height, width=width, fields=fields,
+                is_bigendian=bool(big), point_step=point_step, row_step=row_step, data=data, is_dense=bool(dense))
+
+
+def deserialize_float64_multiarray(buf):
+    """Inverse of serialize_float64_multiarray (any layout) -> (dims [(label, size, stride)], data_offset, float64 array)."""
+    pos = 0
+    (nd,) = struct.unpack_from("<I", buf, pos)
+    pos += 4
+    dims = []
+    for _ in range(nd):
+        (n,) = struct.unpack_from("<I", buf, pos)
+        label = bytes(buf[pos + 4:pos + 4 + n]).decode("utf-8")
+        pos += 4 + n
+        size, stride = struct.unpack_from("<II", buf, pos)
+        pos += 8
+        dims.append((label, size, stride))
+    data_offset, n = struct.unpack_from("<II", buf, pos)
+    pos += 8
+    if pos + 8 * n != len(buf):
+        raise ValueError("length mismatch")
+    return dims, data_offset, np.frombuffer(buf, "<f8", n, pos).copy()
 
 
 def fill_ros_messages(points, odom7, stamp=None, declare_intensity=False):

@@ -171,3 +171,56 @@ def test_frontend_gmm_masker_end_to_end():
     m = F_.gmm_mask(x1, flow)
     _, odom = F_.frontend(x1, flow, mode=0, in_mask=m)
     assert torch.equal(out["mask"], m.cpu()) and torch.equal(out["odom"], odom.cpu())
+
+
+def test_ros_driver_loops_one_odom_per_cloud_in_order():
+    """f-1: the reference drivers' frame loops (scripts/PointCloudOdometry.py:59-105, _noSeg.py:62-127, ASF/main_sju_occ_ros.py:168-284)
+    behind the rospy stand-in: exactly one `frame_odom1` per `velodyne_points` cloud, in order -- the back end pairs them by
+    arrival (src/lidarOdometry.cpp:145-173) -- with the ROS1 wire bytes carrying the cloud and the GPU pose, and the poses equal
+    to the reference's own pose function on the same static set."""
+    from ssf_slam_b200 import frontend, ros_node, synth, wire
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200.weights import random_init_state_dict
+    frames = synth.make_sequence(900, 5, 2048)
+
+    def check_log(ros, odoms, intensity):
+        assert [t for t, _ in ros.log] == ["velodyne_points", "frame_odom1"] * len(frames) and ros.sleeps == len(frames)
+        assert ros.node == "velodyne_points_odometry_node"
+        for k, (cloud, odom) in enumerate(zip(ros.topic("velodyne_points"), ros.topic("frame_odom1"))):
+            d = wire.deserialize_pointcloud2(cloud)
+            assert d["seq"] == k + 1 and d["data"] == frames[k]["pos1"].tobytes() and len(d["fields"]) == (4 if intensity else 3)
+            assert d["point_step"] == 12 and d["frame_id"] == "livox_frame"
+            dims, off, data = wire.deserialize_float64_multiarray(odom)
+            assert dims == [] and np.array_equal(data, odoms[k]) and abs(np.linalg.norm(data[3:]) - 1) < 1e-12
+
+    # GT flow + GT mask
+    ros = ros_node.Rosless()
+    odoms = ros_node.run_gt_odometry(ros, frames)
+    check_log(ros, odoms, intensity=False)
+    for k, it in enumerate(frames):
+        R, t = ofe.reference_pose(it["pos1"], it["gt"], ofe.gt_background(it["s_fg_mask"]))
+        ref_msg = ofe.odom_message(R, t)
+        assert np.abs(odoms[k][:3] - ref_msg[:3]).max() < 1e-4
+        assert min(np.abs(odoms[k][3:] - ref_msg[3:]).max(), np.abs(odoms[k][3:] + ref_msg[3:]).max()) < 1e-5
+    lines = wire.integrate_odometry(odoms)     # the back end's integration of what was published -> TUM trajectory
+    assert len(lines) == len(frames) + 1 and all(len(ln.split()) == 8 for ln in lines)
+    # stored flow + the reference's GMM masker
+    ros = ros_node.Rosless()
+    odoms_g = ros_node.run_noseg_odometry(ros, frames)
+    check_log(ros, odoms_g, intensity=False)
+    for k, it in enumerate(frames):
+        assert np.array_equal(odoms_g[k], frontend.odometry(it["pos1"], it["gt"], masker="gmm")["odom"])
+    # network flow + mask + pose, pipelined over two slots: same payloads as the synchronous front end, frame by frame
+    net = TFlow()
+    net.load_state_dict(random_init_state_dict(0))
+    ros = ros_node.Rosless()
+    odoms_n = ros_node.run_scene_flow_odometry(ros, SceneFlowFrontEnd(net, n_slots=2), frames)
+    check_log(ros, odoms_n, intensity=True)
+    fe = SceneFlowFrontEnd(net, n_slots=1)
+    for k, it in enumerate(frames):
+        assert np.array_equal(odoms_n[k], fe.process(it["pos1"][None], it["pos2"][None])["odom"][0].numpy())
+    # Seg variant: labels go in with every frame
+    ros = ros_node.Rosless()
+    odoms_s = ros_node.run_scene_flow_odometry(ros, SceneFlowFrontEnd(net, n_slots=2, movable=synth.MOVABLE_CLASSES), frames, seg=True)
+    check_log(ros, odoms_s, intensity=True)

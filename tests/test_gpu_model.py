@@ -70,8 +70,12 @@ def setup8k(golden_dir, oracle_c):
     pc1 = torch.from_numpy(g["pos1"].T.copy()).unsqueeze(0)
     pc2 = torch.from_numpy(g["pos2"].T.copy()).unsqueeze(0)
     (flows, fps), inter = tp.tflow_forward(sd, pc1, pc2, return_intermediates=True)
-    for i in range(4):   # the port at this size is the golden (written by the unmodified reference), bit for bit
-        assert np.array_equal(flows[i][0].numpy(), g["flow%d" % i])
+    # the port on THIS host's CPU against the golden the unmodified reference wrote in the build container: bit-identical there
+    # (oracle/gen_golden.py asserts it), last-ulp differences of the CPU's conv kernels elsewhere
+    for i in range(4):
+        assert float(np.abs(flows[i][0].numpy() - g["flow%d" % i]).max()) <= 1e-5
+    for i in range(3):
+        assert np.array_equal(fps[i][0].numpy(), g["fps%d" % (i + 1)])
     return dict(sd=sd, inter=inter, W=prepare_weights(sd, torch.device("cuda:0")))
 
 

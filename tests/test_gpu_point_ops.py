@@ -200,7 +200,8 @@ def test_knn_blocks_equals_brute_force(B, Nq, Nr, k, dup, off):
     assert torch.equal(d0, d1)
 
 
-@pytest.mark.parametrize("B,L,C,n_seg,hot", [(2, 4096, 64, 300, False), (1, 3000, 128, 50, True), (2, 1000, 5, 400, False), (1, 64, 256, 7, True)])
+@pytest.mark.parametrize("B,L,C,n_seg,hot", [(2, 4096, 64, 300, False), (1, 3000, 128, 50, True), (2, 1000, 5, 400, False), (1, 64, 256, 7, True),
+                                             (1, 40000, 8, 10, True)])
 def test_segment_softmax_sum_fused(B, L, C, n_seg, hot):
     """Backward-cost kernel (softmax over each segment's logits, weighted sum of its rows) vs the dense definition;
     `hot` concentrates rows on a few keys so that segments exceed one warp batch (32 rows)."""

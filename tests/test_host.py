@@ -70,6 +70,65 @@ def test_wire_formats():
     assert np.allclose(last[1:4], [1, 1, 0], atol=1e-9)  # second step moves along the rotated x axis
 
 
+def test_ros1_wire_bytes_hand_derived():
+    """B-wire: full ROS1 serialisation of the two messages.  The expected bytes are written out by hand from the message
+    definitions (sensor_msgs/PointCloud2.msg, std_msgs/Header.msg, sensor_msgs/PointField.msg, std_msgs/Float64MultiArray.msg,
+    std_msgs/MultiArrayLayout.msg; genpy: little endian, uint32 length prefixes, uint8 bools), not produced by the serialiser."""
+    from ssf_slam_b200 import wire
+    pts = np.array([[1.0, 2.0, 3.0], [-0.5, 0.25, 100.0]], np.float32)
+    got = wire.serialize_pointcloud2(pts, seq=7, stamp=(1700000000, 5), declare_intensity=False)
+    want = bytes.fromhex(
+        "07000000" "00f15365" "05000000"                    # header.seq = 7, stamp.secs = 1700000000 (0x6553F100), stamp.nsecs = 5
+        "0b000000" + b"livox_frame".hex() +                 # header.frame_id: uint32 length 11 + characters
+        "01000000" "02000000"                               # height = 1, width = 2
+        "03000000"                                          # fields: 3 entries
+        "01000000" "78" "00000000" "07" "01000000"          #   name "x", offset 0, datatype FLOAT32 (7), count 1
+        "01000000" "79" "04000000" "07" "01000000"          #   name "y", offset 4
+        "01000000" "7a" "08000000" "07" "01000000"          #   name "z", offset 8
+        "00"                                                # is_bigendian = False
+        "0c000000" "18000000"                               # point_step = 12, row_step = 24
+        "18000000"                                          # data: 24 bytes
+        "0000803f" "00000040" "00004040"                    #   1.0, 2.0, 3.0
+        "000000bf" "0000803e" "0000c842"                    #   -0.5, 0.25, 100.0
+        "00")                                               # is_dense = False
+    assert got == want
+    d = wire.deserialize_pointcloud2(got)
+    assert d["seq"] == 7 and d["stamp"] == (1700000000, 5) and d["frame_id"] == "livox_frame" and d["width"] == 2
+    assert np.array_equal(np.frombuffer(d["data"], "<f4").reshape(2, 3), pts)
+    # the ASF drivers declare a 4th field `intensity` at offset 12 while keeping point_step = 12 (main_sju_occ_ros.py:243-250)
+    got4 = wire.serialize_pointcloud2(pts, seq=1, stamp=(0, 0), declare_intensity=True)
+    extra = bytes.fromhex("09000000" + b"intensity".hex() + "0c000000" "07" "01000000")
+    assert len(got4) == len(got) + len(extra) and extra in got4
+    assert struct.unpack_from("<I", got4, 12 + 4 + 11 + 8)[0] == 4       # field count, after header (12 + string) and height/width
+    with pytest.raises(ValueError):
+        wire.deserialize_pointcloud2(got + b"\x00")
+    with pytest.raises(ValueError):
+        wire.deserialize_pointcloud2(got[:-3])
+    # frame_odom1: Float64MultiArray with an empty layout
+    o = [0.5, -2.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+    want_o = bytes.fromhex("00000000" "00000000" "07000000"             # layout.dim: 0 entries; layout.data_offset = 0; 7 doubles
+                           "000000000000e03f" "00000000000000c0" "0000000000000000" "0000000000000000"
+                           "0000000000000000" "0000000000000000" "000000000000f03f")
+    assert wire.serialize_float64_multiarray(o) == want_o
+    dims, off, data = wire.deserialize_float64_multiarray(want_o)
+    assert dims == [] and off == 0 and data.tolist() == o
+
+
+def test_ros_node_loops_without_ros():
+    """f-1: the drivers' frame loops behind the rospy stand-in: node name, topics, one cloud per frame with rospy's header.seq
+    stamping and the simulated 10 Hz clock, ROS1 wire bytes of every message (PointCloudOdometry_onlyPC.py:36-66)."""
+    from ssf_slam_b200 import ros_node, synth, wire
+    frames = synth.make_sequence(5, 3, 256)
+    ros = ros_node.Rosless()
+    assert ros_node.run_pointcloud_only(ros, frames) == 3
+    assert ros.node == "velodyne_points_node" and [t for t, _ in ros.log] == ["velodyne_points"] * 3 and ros.sleeps == 3
+    for k, raw in enumerate(ros.topic("velodyne_points")):
+        d = wire.deserialize_pointcloud2(raw)
+        assert d["seq"] == k + 1 and d["stamp"] == (k // 10, (k % 10) * 100_000_000) and d["width"] == 256 and d["height"] == 1
+        assert d["point_step"] == 12 and d["row_step"] == 12 * 256 and not d["is_dense"] and len(d["fields"]) == 3
+        assert d["data"] == frames[k]["pos1"].tobytes()
+
+
 def test_synthetic_generator_shapes_and_determinism():
     from ssf_slam_b200 import synth
     a, b = synth.make_pair(0, 1024), synth.make_pair(0, 1024)
@@ -114,19 +173,37 @@ def test_sharding_and_final_gather_gloo_world2():
         assert r[2] == [0.0, 1.0] and r[3] == [0, 1]
 
 
-def test_carla_subsampler_matches_reference_golden():
-    """f-2: our loader/subsampler reproduces the UNMODIFIED reference method's output (golden written by
-    oracle/gen_golden_dataset.py, which calls CARLA3D.subsample_points itself) under the same NumPy seed."""
-    import os
+CARLA_CASES = (("default", 512, {}), ("noseg_rmground", 1024, dict(pre_segfrnt=False, rm_ground=True)),
+               ("small_replace", 1024, dict(pre_segfrnt=True)), ("hybrid", 1024, dict(hybrid_sample=True)))
+
+
+def check_carla_subsampler(ops, golden_path):
+    """f-2: the subsampler reproduces the UNMODIFIED reference method's output (golden written by oracle/gen_golden_dataset.py,
+    which calls CARLA3D.subsample_points itself) under the same NumPy seed, for four flag settings incl. hybrid fg/bg sampling."""
     from ssf_slam_b200 import dataset
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "carla_subsample.npz"))
+    g = np.load(golden_path)
     frame = {k: g[k] for k in ("pos1", "pos2", "ego_flow", "gt", "s_fg_mask", "t_fg_mask")}
-    cases = (("default", 512, {}), ("noseg_rmground", 1024, dict(pre_segfrnt=False, rm_ground=True)),
-             ("small_replace", 1024, dict(pre_segfrnt=True)), ("hybrid", 1024, dict(hybrid_sample=True)))
-    for tag, nb, flags in cases:
-        seq, gt, mask = dataset.load_sequence(frame)
+    dev = dataset.DeviceFrame(*dataset.load_sequence(frame), ops=ops)     # uploaded once, subsampled four times
+    for tag, nb, flags in CARLA_CASES:
         np.random.seed(1234)
-        s, t, m = dataset.subsample_points(seq, gt, mask, nb, **flags)
+        s, t, m = dataset.subsample_points(dev, nb, **flags)
         for name, got in (("pos1", s[0]), ("pos2", s[1]), ("ego", t[0]), ("gt", t[1]), ("m0", m[0]), ("m1", m[1])):
-            assert np.array_equal(got, g[tag + "_" + name]), (tag, name)
+            assert np.array_equal(got.cpu().numpy(), g[tag + "_" + name]), (tag, name)
+    batch = dataset.device_batch([dataset.subsample_points(dev, 256), dataset.subsample_points(dev, 256)])
+    assert batch["pos1"].shape == (2, 256, 3) and batch["s_fg_mask"].shape == (2, 256) and batch["gt"].shape == (2, 256, 3)
     assert frame["pos1"].shape == (3000, 3)   # inputs untouched
+
+
+def test_carla_subsampler_host_logic_matches_reference_golden(golden_dir):
+    """CPU: the host logic (np.random call order, index-list algebra) over a NumPy stand-in for the device primitives."""
+    from numpy_ops import NumpyOps
+    check_carla_subsampler(NumpyOps(), os.path.join(golden_dir, "carla_subsample.npz"))
+
+
+@pytest.mark.gpu
+def test_carla_subsampler_on_device_matches_reference_golden(golden_dir):
+    """GPU: the same through the CUDA kernels (csrc/dataset.cu): stable compaction, index composition, row / byte gathers."""
+    from ssf_slam_b200 import dataset
+    check_carla_subsampler(dataset.CudaOps(), os.path.join(golden_dir, "carla_subsample.npz"))
+    with pytest.raises(ValueError):
+        dataset.DeviceFrame([np.zeros((4, 3), np.float32)] * 2, [np.zeros((4, 3), np.float32)] * 2, [np.full(4, 0.5), np.zeros(4)])

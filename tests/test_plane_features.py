@@ -1,5 +1,11 @@
 """f-3: plane-feature extraction after src/frameFeature.cpp:45-127.
-CPU: the two oracle restatements (C, Python) agree.  GPU: the kernel equals the C oracle bit for bit."""
+Pinned: tests/golden/plane_features_ref.npz holds what the reference's OWN node publishes -- src/frameFeature.cpp compiled
+unmodified into oracle/_ref/libframe_feature_ref.so (oracle/ref_build/, oracle/gen_golden_plane_features.py).
+CPU: the oracle restatements (C, Python) reproduce the golden (and the compiled node itself when oracle/_ref is present).
+GPU: the kernel equals the golden and the C oracle bit for bit."""
+import ctypes
+import os
+
 import numpy as np
 import pytest
 
@@ -24,6 +30,38 @@ def lidar_cloud(seed, n, n_rows):
     pts[5] = 0                                    # origin: angle NaN -> dropped
     pts[6, :2] = 0                                # vertical: +-90 degrees -> out of range
     return pts
+
+
+def _golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "plane_features_ref.npz"))
+    return [(g["pts%d" % k], int(g["rows%d" % k]), g["ref%d" % k]) for k in range(int(g["n"]))]
+
+
+def test_oracle_matches_compiled_reference_node(golden_dir, oracle_c):
+    """The C oracle (every cloud) and the Python oracle (the 3000-point clouds) against the outputs of the compiled reference
+    node; when the node's library is present (build container; it also travels to the GPU box) it is called live as well."""
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libframe_feature_ref.so")
+    lib = ctypes.CDLL(ref) if os.path.exists(ref) else None
+    for pts, n_rows, want in _golden(golden_dir):
+        assert np.array_equal(opf.plane_features_c(pts, n_rows), want)
+        if pts.shape[0] <= 3000:
+            assert np.array_equal(opf.plane_features_py(pts, n_rows), want)
+        if lib is not None:
+            out = np.zeros((pts.shape[0], 4), np.float32)
+            cnt = ctypes.c_int(0)
+            P = np.ascontiguousarray(pts, np.float32)
+            assert lib.ssf_ref_plane_features(ctypes.c_void_p(P.ctypes.data), P.shape[0], n_rows, ctypes.c_void_p(out.ctypes.data), ctypes.byref(cnt)) == 0
+            assert np.array_equal(out[:cnt.value], want)
+
+
+@pytest.mark.gpu
+def test_plane_features_gpu_equals_compiled_reference_node(golden_dir):
+    import torch
+    from ssf_slam_b200.plane_features import plane_features
+    for pts, n_rows, want in _golden(golden_dir):
+        out, cnt = plane_features(torch.from_numpy(pts[None]).cuda(), n_rows)
+        out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+        assert cnt[0] == want.shape[0] and np.array_equal(out[0, :cnt[0]], want)
 
 
 @pytest.mark.parametrize("n_rows,n", [(16, 700), (64, 1500)])

@@ -291,10 +291,10 @@ def point_op_rooflines(B, N, dev):
         lambda: pu.grouping_operation(feat96, idx16))
     hbm("three_interpolate[C=96,n=%d]" % N, B * (4.0 * 3 * N * 2 + 4.0 * C * N * 3 + 4.0 * C * N), B * (4.0 * 3 * N * 2 + 8.0 * C * N),
         lambda: pu.three_interpolate(feat96, idx3, w3))
-    # gather_operation: compulsory DRAM = every 32-byte sector that holds a gathered element + indices + output.  With M of N
-    # columns picked (FPS: spread out), almost every picked element sits in its own sector, so the read stream is 32 B per
-    # 4-byte element: `dram` counts 32*C*M for the reads, `byts` the algorithmic 4*C*M.
-    hbm("gather_operation[C=96,M=%d]" % M, B * (4.0 * M + 8.0 * C * M), B * (4.0 * M + 32.0 * C * M + 4.0 * C * M),
+    # gather_operation: compulsory DRAM reads are whole 32-byte sectors: min(32 M, 4 N) bytes per channel row (with M = N / 4 FPS
+    # picks spread over the row nearly every sector holds a picked element, so the row is read once: ncu measures 202 MB read for
+    # these 64 clouds = 64 x 96 x 8192 x 4, profiles/ncu_traffic.json); `byts` stays the algorithmic 4 M + 8 C M of SURVEY 8(d)
+    hbm("gather_operation[C=96,M=%d]" % M, B * (4.0 * M + 8.0 * C * M), B * (4.0 * M + min(32.0 * M, 4.0 * N) * C + 4.0 * C * M),
         lambda: pu.gather_operation(feat96, fps_idx))
     rate("furthest_point_sample[N=%d,n=%d]" % (N, M), B * float(N) * M, "G point-updates/s", lambda: pu.furthest_point_sample(xyz, M))
     rate("knn[k=16,%dx%d]" % (N, N), B * float(N) * N, "G pair-evaluations/s (brute-force equivalent)", lambda: pu.knn(16, xyz, xyz))

@@ -142,9 +142,10 @@ void ssf_oracle_group(const float *feat, const int32_t *idx, int B, int C, int N
     }
 }
 
-/* ---- plane-feature extraction: restatement of src/frameFeature.cpp:45-127 (test infrastructure; parity unpinned: the
- * node cannot be compiled here -- ROS / PCL absent -- so this follows the source line by line: float/double types of
- * every sub-expression as C++ would evaluate them with the <cmath> float overloads).
+/* ---- plane-feature extraction: restatement of src/frameFeature.cpp:45-127 (test infrastructure).  Pinned: the node itself
+ * compiles unmodified against stand-in ROS / PCL headers (oracle/ref_build/ -> oracle/_ref/libframe_feature_ref.so) and
+ * oracle/gen_golden_plane_features.py asserts this restatement equals what it publishes, bit for bit.  Float/double types of
+ * every sub-expression are those C++ evaluates with the <math.h> float overloads.
  * points [N,3]; out [N,4]; returns the number of plane points.  tmp: N ints + N ints + N floats + N ints. */
 int ssf_oracle_plane_features(const float* P, int N, int n_rows, int row_start, int row_end, float plane_min, int plane_span,
                               float* out) {

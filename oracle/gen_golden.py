@@ -10,7 +10,8 @@ Pins the oracle and writes the committed fixtures under tests/golden/:
    is exec'd verbatim and compared with oracle.frontend.solve_rt_svd; stored with inputs.
 3. point_ops.npz -- small clouds with exact duplicates: FPS / kNN / 3-NN / ball-query results of the C and
    the torch restatements (which must agree).  The extension is absent from the reference, so these pin
-   the written tie-breaking spec only ("parity unpinned").
+   the written tie-breaking spec; the tie-free behaviour is pinned against the reference's own pure-torch twins by
+   oracle/gen_golden_point_twins.py (tests/golden/point_twins.npz).
 4. masker.npz -- oracle.frontend.masker_spec on a synthetic frame with gt flow (+ noise), noSeg and Seg.
 
 Usage:  python -m oracle.gen_golden

@@ -21,9 +21,13 @@ tie-breaking spec written down in SURVEY.md Appendix C:
 * grouping / gather -- as called at ``ASF/utils/utils.py:228-233``
 * scatter_softmax / scatter_sum -- as called at ``ASF/utils/soflow.py:474,481`` (dim=1)
 
-PARITY UNPINNED: the reference has no tests or golden vectors for these operators; the
-fixtures under tests/golden/ are produced by running this oracle underneath the
-reference's unmodified model code (oracle/gen_golden.py).
+PINNED on tie-free data: oracle/gen_golden_point_twins.py executes the reference's own in-tree
+pure-torch twins of the extension unmodified -- ``farthest_point_sample`` / ``knn_point``
+(``ASF/utils/utils.py:68-108``) and ``query_ball_point`` (``ASF/SetCover.py:39-63``) -- and asserts
+that both restatements here (torch and plain C) return the same indices; the vectors are committed
+as tests/golden/point_twins.npz.  What stays a WRITTEN specification (the extension itself is absent
+from the reference, which has no tests for it) is the behaviour on exact ties -- lowest index first --
+and the no-FMA distance arithmetic; tests/golden/point_ops.npz pins those between the two restatements.
 """
 import numpy as np
 import torch

@@ -10,7 +10,8 @@ Pinned: oracle/gen_golden.py runs the UNMODIFIED reference model (imported from
 /root/reference over the oracle shims) and this port on the same seeded weights and clouds and
 asserts bit-identical flows and FPS indices; the resulting vectors are committed under
 tests/golden/.  The point operators underneath are the oracle's (oracle/point_ops.py; the
-extension itself is absent from the reference, so their tie-breaking is "parity unpinned").
+extension itself is absent from the reference; pinned against the reference's in-tree pure-torch
+twins on tie-free data, tie-breaking by written specification -- see oracle/point_ops.py).
 
 Reference lines followed, per function, are cited in each docstring.  Layout is the
 reference's: features ``[B,C,N]``, coordinates ``[B,3,N]``.

@@ -27,7 +27,11 @@ __device__ unsigned long long g_knn_stat[4];   // queries, visits, inserts, swee
 namespace {
 
 constexpr int KB_BUILD_T = 1024;
-constexpr int KB_QPB = 64;   // queries per search CTA (8 warps x 8)
+// Search CTAs are small (4 warps, <= 40 registers per thread, 8 KB of shared memory) ON PURPOSE: one such CTA still fits on an SM
+// that a persistent tensor-core CTA of another stream occupies (cost volume: 576 threads x 96 registers, 207 KB), so the searches
+// of one batch run in the issue slots the tensor kernels of another batch leave idle (they issue ~40 % of the time).
+constexpr int KB_SEARCH_T = 128;                       // threads per search CTA
+constexpr int KB_QPB = (KB_SEARCH_T / 32) * 8;         // queries per search CTA (8 per warp)
 
 __device__ __forceinline__ unsigned morton_spread(unsigned v) {   // 10 bits -> every third bit
     v = (v | (v << 16)) & 0x030000FFu;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
 }
 
 template <int NBL>
-__global__ void __launch_bounds__(256, 6) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
+__global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
                                                                 const float* __restrict__ ws, int Nq, int npad, int nblk,
                                                                 float* __restrict__ dist, int* __restrict__ idx) {
     // survivors of a block from which the sort-merge beats one-by-one insertion (measured: 6 for <= 64 blocks, 10-16 above)
@@ -155,11 +159,11 @@ __global__ void __launch_bounds__(256, 6) knn_blocks_search_kernel(int k, const 
     const float4* P = reinterpret_cast<const float4*>(wsb);
     {
         const float4* src = P + npad;
-        for (int i = tid; i < 2 * nblk; i += 256) sbox[i] = __ldg(src + i);
+        for (int i = tid; i < 2 * nblk; i += KB_SEARCH_T) sbox[i] = __ldg(src + i);
     }
     __syncthreads();
     const int q_end = min(Nq, (int)(blockIdx.x + 1) * KB_QPB);
-    for (int qi = blockIdx.x * KB_QPB + warp; qi < q_end; qi += 8) {
+    for (int qi = blockIdx.x * KB_QPB + warp; qi < q_end; qi += KB_SEARCH_T / 32) {
         const float* qp = query + ((size_t)b * Nq + qi) * 3;
         float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
         if (qadd != nullptr) {
@@ -430,11 +434,11 @@ extern "C" int ssf_knn_blocks_search(int k, const float* query, const float* que
     dim3 grid((Nq + KB_QPB - 1) / KB_QPB, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (nblk <= 64)
-        knn_blocks_search_kernel<2><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+        knn_blocks_search_kernel<2><<<grid, KB_SEARCH_T, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
     else if (nblk <= 256)
-        knn_blocks_search_kernel<8><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+        knn_blocks_search_kernel<8><<<grid, KB_SEARCH_T, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
     else
-        knn_blocks_search_kernel<16><<<grid, 256, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+        knn_blocks_search_kernel<16><<<grid, KB_SEARCH_T, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

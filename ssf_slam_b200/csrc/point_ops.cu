@@ -199,7 +199,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int npoint, int* __rest
 template <int T, int PPT>
 static int launch_fps(const float* xyz, int B, int N, int npoint, int* out, cudaStream_t st) {
     size_t smem = (size_t)N * 3 * sizeof(float);
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {   // the 48 KB default covers static + dynamic shared memory: opt in with room for the static part
         cudaError_t e = cudaFuncSetAttribute(fps_kernel<T, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return ssf_set_error(e);
     }

@@ -64,7 +64,7 @@ def test_reference_twins_golden(pu, golden_dir):
 
 
 @pytest.mark.parametrize("N,npoint", [(8192, 2048), (2048, 512), (512, 256), (256, 128), (100, 37), (1, 1), (5000, 300),
-                                      (130, 140), (16384, 1024), (20000, 512), (65536, 2048)])
+                                      (130, 140), (16384, 1024), (20000, 512), (65536, 2048), (4096, 512), (4000, 100), (3500, 64)])
 def test_fps(pu, N, npoint):
     B = 3 if N <= 8192 else 2
     x = _cloud(N, B, N)

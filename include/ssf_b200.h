@@ -46,7 +46,8 @@ int ssf_knn_offset(int k, const float* query, const float* query_add, const floa
                    float* dist, int* idx, void* stream);
 
 /* Same result as ssf_knn_offset, bit for bit, through a spatial index: `build` Morton-sorts each reference cloud into
- * blocks of 32 points with bounding boxes (workspace of ssf_knn_blocks_workspace_floats(B,Nr) floats, Nr <= 16384),
+ * blocks of 32 points with bounding boxes (workspace of ssf_knn_blocks_workspace_floats(B,Nr) floats, Nr <= 131072; above
+ * 16384 points the sort is a global-memory radix sort and super-blocks of 32 blocks add a second level),
  * `search` walks the blocks nearest-first and stops when no remaining box can hold a closer point. */
 long long ssf_knn_blocks_workspace_floats(int B, int Nr);
 int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, void* stream);

@@ -384,6 +384,311 @@ __global__ void __launch_bounds__(256) knn_warp_scan_kernel(int k, const float* 
     }
 }
 
+
+// ------------------------------------------------------------------ clouds above 16384 points (BASELINE config 5: N = 65536)
+// The Morton sort no longer fits in shared memory, and one lane cannot hold the bounds of all blocks.  So:
+//  build : one CTA per cloud, stable LSD radix sort of the (key, index) pairs in global scratch (eight 4-bit passes; thread t
+//          owns a contiguous chunk, per-(digit, thread) counters in shared memory, one block scan per pass -- stable, so equal
+//          keys stay in index order and the layout is the same deterministic function of the cloud as the bitonic build's),
+//          then the same sorted float4 points + per-block boxes, plus the boxes of SUPER-BLOCKS of 32 consecutive blocks.
+//  search: two levels.  A lane owns the bounds of <= 4 super-blocks; the warp pops super-blocks nearest-first while their bound
+//          does not exceed the k-th distance, and inside a popped super-block lane l owns block l: the nearest few blocks are
+//          visited first, the rest in index order while their bound does not exceed the (shrinking) k-th distance.  Same
+//          keys, same list operations, same strict-skip rule as the one-level search: bit-identical to the brute-force scan.
+// ws layout per cloud (floats): pts4 [npad][4] | box_lo [nblk][4] | box_hi [nblk][4] | sb_lo [nsb][4] | sb_hi [nsb][4] | scratch [4 npad]
+constexpr int KB_RADIX_T = 1024;
+
+__global__ void __launch_bounds__(KB_RADIX_T) knn_blocks_build_large_kernel(const float* __restrict__ ref, int Nr, int npad, int nblk,
+                                                                            int nsb, long long ws_per_cloud, float* __restrict__ ws) {
+    extern __shared__ __align__(16) int s_cnt[];          // [16][KB_RADIX_T]
+    __shared__ float sred[6][32];
+    __shared__ float sbb[6];
+    __shared__ int s_scan[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* rp = ref + (size_t)blockIdx.x * Nr * 3;
+    float* wsb = ws + (size_t)blockIdx.x * ws_per_cloud;
+    float4* pts4 = reinterpret_cast<float4*>(wsb);
+    float4* blo = pts4 + npad;
+    float4* bhi = blo + nblk;
+    float4* slo = bhi + nblk;
+    float4* shi = slo + nsb;
+    unsigned* keyA = reinterpret_cast<unsigned*>(shi + nsb);
+    unsigned* keyB = keyA + npad;
+    int* valA = reinterpret_cast<int*>(keyB + npad);
+    int* valB = valA + npad;
+    // cloud bounding box
+    float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int i = tid; i < Nr; i += KB_RADIX_T)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = rp[3 * i + c];
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+        if (lane == 0) {
+            sred[c][warp] = mn[c];
+            sred[3 + c][warp] = mx[c];
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float v = sred[tid][0];
+        for (int w = 1; w < KB_RADIX_T / 32; ++w) v = tid < 3 ? fminf(v, sred[tid][w]) : fmaxf(v, sred[tid][w]);
+        sbb[tid] = v;
+    }
+    __syncthreads();
+    float sc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ext = sbb[3 + c] - sbb[c];
+        sc[c] = ext > 0.f ? 1023.0f / ext : 0.f;
+    }
+    for (int i = tid; i < npad; i += KB_RADIX_T) {
+        unsigned key = 0xFFFFFFFFu;      // padding sorts last (real keys have 30 bits)
+        if (i < Nr) {
+            unsigned q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float t = (rp[3 * i + c] - sbb[c]) * sc[c];
+                q[c] = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
+            }
+            key = morton_spread(q[0]) | (morton_spread(q[1]) << 1) | (morton_spread(q[2]) << 2);
+        }
+        keyA[i] = key;
+        valA[i] = i;
+    }
+    __syncthreads();
+    // stable LSD radix sort, 4 bits per pass; thread t owns elements [t * chunk, t * chunk + chunk)
+    const int chunk = (npad + KB_RADIX_T - 1) / KB_RADIX_T;
+    const int e0 = min(npad, tid * chunk), e1 = min(npad, e0 + chunk);
+    unsigned* kin = keyA; unsigned* kout = keyB;
+    int* vin = valA; int* vout = valB;
+    for (int shift = 0; shift < 32; shift += 4) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) s_cnt[d * KB_RADIX_T + tid] = 0;
+        for (int e = e0; e < e1; ++e) s_cnt[((kin[e] >> shift) & 15u) * KB_RADIX_T + tid] += 1;
+        __syncthreads();
+        // exclusive scan of the 16 * KB_RADIX_T counters in (digit, thread) order: thread t scans entries [16 t, 16 t + 16)
+        int loc[16], sum = 0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            loc[u] = sum;
+            sum += s_cnt[tid * 16 + u];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_scan[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_scan[lane] = w;
+        }
+        __syncthreads();
+        const int base = inc - sum + (warp > 0 ? s_scan[warp - 1] : 0);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s_cnt[tid * 16 + u] = base + loc[u];
+        __syncthreads();
+        for (int e = e0; e < e1; ++e) {
+            const unsigned kk = kin[e];
+            const int pos = s_cnt[((kk >> shift) & 15u) * KB_RADIX_T + tid]++;
+            kout[pos] = kk;
+            vout[pos] = vin[e];
+        }
+        __syncthreads();
+        unsigned* tk = kin; kin = kout; kout = tk;
+        int* tv = vin; vin = vout; vout = tv;
+    }
+    // sorted points (padding: +inf coordinates, index INT_MAX -> never selected) and per-block boxes (after 8 passes: in A)
+    for (int i = tid; i < npad; i += KB_RADIX_T) {
+        float4 p = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(0x7fffffff));
+        float lo3[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi3[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        const int o = vin[i];
+        if (o < Nr && kin[i] != 0xFFFFFFFFu) {
+            p = make_float4(rp[3 * o], rp[3 * o + 1], rp[3 * o + 2], __int_as_float(o));
+            lo3[0] = hi3[0] = p.x; lo3[1] = hi3[1] = p.y; lo3[2] = hi3[2] = p.z;
+        }
+        pts4[i] = p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                lo3[c] = fminf(lo3[c], __shfl_xor_sync(0xffffffffu, lo3[c], o2));
+                hi3[c] = fmaxf(hi3[c], __shfl_xor_sync(0xffffffffu, hi3[c], o2));
+            }
+        if (lane == 0) {
+            blo[i >> 5] = make_float4(lo3[0], lo3[1], lo3[2], 0.f);
+            bhi[i >> 5] = make_float4(hi3[0], hi3[1], hi3[2], 0.f);
+        }
+    }
+    __syncthreads();   // block boxes (global, written by this CTA) are read back below
+    for (int sb = warp; sb < nsb; sb += KB_RADIX_T / 32) {
+        const int blk = sb * 32 + lane;
+        float lo3[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi3[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        if (blk < nblk) {
+            const float4 l = blo[blk], h = bhi[blk];
+            lo3[0] = l.x; lo3[1] = l.y; lo3[2] = l.z; hi3[0] = h.x; hi3[1] = h.y; hi3[2] = h.z;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                lo3[c] = fminf(lo3[c], __shfl_xor_sync(0xffffffffu, lo3[c], o2));
+                hi3[c] = fmaxf(hi3[c], __shfl_xor_sync(0xffffffffu, hi3[c], o2));
+            }
+        if (lane == 0) {
+            slo[sb] = make_float4(lo3[0], lo3[1], lo3[2], 0.f);
+            shi[sb] = make_float4(hi3[0], hi3[1], hi3[2], 0.f);
+        }
+    }
+}
+
+template <int NSB>
+__global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search2_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
+                                                                            const float* __restrict__ ws, long long ws_per_cloud, int Nq, int npad,
+                                                                            int nblk, int nsb, float* __restrict__ dist, int* __restrict__ idx) {
+    extern __shared__ __align__(16) float4 sbox[];   // [nsb] lo | [nsb] hi of the super-blocks
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const float* wsb = ws + (size_t)b * ws_per_cloud;
+    const float4* P = reinterpret_cast<const float4*>(wsb);
+    const float4* BLO = P + npad;
+    const float4* BHI = BLO + nblk;
+    {
+        const float4* src = BHI + nblk;
+        for (int i = tid; i < 2 * nsb; i += KB_SEARCH_T) sbox[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    auto box_bound = [](const float4 lo, const float4 hi, float qx, float qy, float qz) -> float {
+        const float gx = fmaxf(0.f, fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)));
+        const float gy = fmaxf(0.f, fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)));
+        const float gz = fmaxf(0.f, fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)));
+        return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+    };
+    const int q_end = min(Nq, (int)(blockIdx.x + 1) * KB_QPB);
+    for (int qi = blockIdx.x * KB_QPB + warp; qi < q_end; qi += KB_SEARCH_T / 32) {
+        const float* qp = query + ((size_t)b * Nq + qi) * 3;
+        float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        if (qadd != nullptr) {
+            const float* ap = qadd + ((size_t)b * Nq + qi) * 3;
+            qx = __fadd_rn(qx, __ldg(ap));
+            qy = __fadd_rn(qy, __ldg(ap + 1));
+            qz = __fadd_rn(qz, __ldg(ap + 2));
+        }
+        float slb[NSB];
+#pragma unroll
+        for (int s = 0; s < NSB; ++s) {
+            const int sb = s * 32 + lane;
+            slb[s] = sb < nsb ? box_bound(sbox[sb], sbox[nsb + sb], qx, qy, qz) : CUDART_INF_F;
+        }
+        unsigned long long list_k = 0x7f8000007fffffffull, kth = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+        float kth_d = CUDART_INF_F;
+        auto pack = [](float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; };
+        auto sort32 = [&](unsigned long long key) -> unsigned long long {
+#pragma unroll
+            for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                    if (take_min == (ok < key)) key = ok;
+                }
+            }
+            return key;
+        };
+        auto visit = [&](int blk) {
+            const float4 p = __ldg(P + (size_t)blk * 32 + lane);
+            unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+            unsigned mask = __ballot_sync(0xffffffffu, key < kth);
+            if (__popc(mask) >= 12) {
+                key = sort32(key);
+                const unsigned long long rev = __shfl_sync(0xffffffffu, key, 31 - lane);
+                unsigned long long m = rev < list_k ? rev : list_k;
+#pragma unroll
+                for (int j = 16; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, m, j);
+                    if (((lane & j) == 0) == (ok < m)) m = ok;
+                }
+                list_k = m;
+                kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+            } else {
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
+                    if (ck >= kth) continue;   // warp-uniform: the k-th key tightened meanwhile
+                    const int pos = __popc(__ballot_sync(0xffffffffu, list_k < ck));
+                    const unsigned long long uk = __shfl_up_sync(0xffffffffu, list_k, 1);
+                    list_k = lane == pos ? ck : (lane > pos ? uk : list_k);
+                    kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+                }
+            }
+            kth_d = __uint_as_float((unsigned)(kth >> 32));
+        };
+        bool first = true;
+#pragma unroll 1
+        for (;;) {
+            // nearest remaining super-block (two integer reductions: bounds are non-negative floats)
+            float best = slb[0];
+            int bs = 0;
+#pragma unroll
+            for (int s = 1; s < NSB; ++s)
+                if (slb[s] < best) {
+                    best = slb[s];
+                    bs = s;
+                }
+            const unsigned mn = __reduce_min_sync(0xffffffffu, __float_as_uint(best));
+            if (__uint_as_float(mn) == CUDART_INF_F || __uint_as_float(mn) > kth_d) break;   // no remaining box can hold a better point
+            const int sb = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(best) == mn ? (unsigned)(bs * 32 + lane) : 0x7fffffffu);
+#pragma unroll
+            for (int s = 0; s < NSB; ++s)
+                if (s == (sb >> 5) && lane == (sb & 31)) slb[s] = CUDART_INF_F;
+            // inside the super-block: lane = block
+            const int blk = sb * 32 + lane;
+            float lbk = CUDART_INF_F;
+            if (blk < nblk) lbk = box_bound(__ldg(BLO + blk), __ldg(BHI + blk), qx, qy, qz);
+            // nearest-first visits tighten the k-th distance quickly (more of them in the first super-block of a query)
+#pragma unroll 1
+            for (int rep = 0; rep < (first ? 4 : 1); ++rep) {
+                const unsigned bm = __reduce_min_sync(0xffffffffu, __float_as_uint(lbk));
+                if (__uint_as_float(bm) == CUDART_INF_F || __uint_as_float(bm) > kth_d) break;
+                const int bl = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(lbk) == bm ? (unsigned)lane : 0x7fffffffu);
+                if (lane == bl) lbk = CUDART_INF_F;
+                visit(sb * 32 + bl);
+            }
+            first = false;
+            unsigned m = __ballot_sync(0xffffffffu, lbk <= kth_d && lbk != CUDART_INF_F);
+            while (m) {
+                const int bl = __ffs(m) - 1;
+                m &= m - 1;
+                const float blb = __shfl_sync(0xffffffffu, lbk, bl);
+                if (blb > kth_d) continue;   // warp-uniform
+                visit(sb * 32 + bl);
+            }
+        }
+        if (lane < k) {
+            const size_t o = ((size_t)b * Nq + qi) * k + lane;
+            idx[o] = (int)(unsigned)(list_k & 0xffffffffull);
+            if (dist != nullptr) dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(list_k >> 32)));
+        }
+    }
+}
+
 inline int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -401,14 +706,34 @@ extern "C" int ssf_knn_stat_read(unsigned long long* out, int reset) {
 #endif
 
 // floats of workspace for B reference clouds of Nr points
-extern "C" long long ssf_knn_blocks_workspace_floats(int B, int Nr) {
+constexpr int KB_ONE_LEVEL_MAX = 16384;    // one-level search / shared-memory bitonic build up to here
+constexpr int KB_MAX_REF = 131072;         // two-level search: <= 128 super-blocks of 1024 points
+
+static long long knn_ws_per_cloud(int Nr) {
     const long long npad = ((long long)Nr + 31) / 32 * 32, nblk = npad / 32;
-    return (long long)B * (npad * 4 + nblk * 8);
+    if (Nr <= KB_ONE_LEVEL_MAX) return npad * 4 + nblk * 8;
+    const long long nsb = (nblk + 31) / 32;
+    return npad * 4 + nblk * 8 + nsb * 8 + npad * 4;   // + super-block boxes + radix-sort scratch (2 x (key, index))
 }
+
+extern "C" long long ssf_knn_blocks_workspace_floats(int B, int Nr) { return (long long)B * knn_ws_per_cloud(Nr); }
 
 extern "C" int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, void* stream) {
     if (B <= 0 || Nr <= 0) return ssf_arg_error("knn_blocks_build: empty input");
-    if (Nr > 16384) return ssf_arg_error("knn_blocks_build: at most 16384 reference points (larger clouds use ssf_knn)");
+    if (Nr > KB_MAX_REF) return ssf_arg_error("knn_blocks_build: at most 131072 reference points");
+    if (Nr > KB_ONE_LEVEL_MAX) {
+        const int npad_l = (Nr + 31) / 32 * 32, nblk_l = npad_l / 32, nsb = (nblk_l + 31) / 32;
+        static unsigned long long attr_l = 0;
+        if (ssf_attr_needed(&attr_l)) {
+            cudaError_t e = cudaFuncSetAttribute(knn_blocks_build_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * KB_RADIX_T * 4);
+            if (e != cudaSuccess) return ssf_set_error(e);
+            ssf_attr_done(&attr_l);
+        }
+        knn_blocks_build_large_kernel<<<B, KB_RADIX_T, 16 * KB_RADIX_T * 4, (cudaStream_t)stream>>>(ref, Nr, npad_l, nblk_l, nsb, knn_ws_per_cloud(Nr), ws);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
     const int npow2 = next_pow2(Nr), npad = (Nr + 31) / 32 * 32, nblk = npad / 32;
     const size_t smem = (size_t)npow2 * 8;
     static unsigned long long attr_set = 0;
@@ -428,11 +753,22 @@ extern "C" int ssf_knn_blocks_search(int k, const float* query, const float* que
     if (B <= 0 || Nq <= 0) return ssf_arg_error("knn_blocks_search: empty input");
     if (k <= 0 || k > 32) return ssf_arg_error("knn: k must be in [1,32]");
     if (k > Nr) return ssf_arg_error("knn: k exceeds the number of reference points");
-    if (Nr > 16384) return ssf_arg_error("knn_blocks_search: at most 16384 reference points");
+    if (Nr > KB_MAX_REF) return ssf_arg_error("knn_blocks_search: at most 131072 reference points");
     const int npad = (Nr + 31) / 32 * 32, nblk = npad / 32;
-    const size_t smem = (size_t)nblk * 32;
     dim3 grid((Nq + KB_QPB - 1) / KB_QPB, B);
     cudaStream_t st = (cudaStream_t)stream;
+    if (Nr > KB_ONE_LEVEL_MAX) {
+        const int nsb = (nblk + 31) / 32;
+        const size_t smem2 = (size_t)nsb * 32;
+        if (nsb <= 64)
+            knn_blocks_search2_kernel<2><<<grid, KB_SEARCH_T, smem2, st>>>(k, query, query_add, ws, knn_ws_per_cloud(Nr), Nq, npad, nblk, nsb, dist, idx);
+        else
+            knn_blocks_search2_kernel<4><<<grid, KB_SEARCH_T, smem2, st>>>(k, query, query_add, ws, knn_ws_per_cloud(Nr), Nq, npad, nblk, nsb, dist, idx);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
+    const size_t smem = (size_t)nblk * 32;
     if (nblk <= 64)
         knn_blocks_search_kernel<2><<<grid, KB_SEARCH_T, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
     else if (nblk <= 256)

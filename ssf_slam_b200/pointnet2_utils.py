@@ -62,8 +62,9 @@ def knn(k, unknown, known, offset=None):
     idx = torch.empty(B, Nq, k, dtype=torch.int32, device=unknown.device)
     off = None if offset is None else _f32(offset)
     L = nat.lib()
-    if 512 <= Nr <= 16384:
-        # Morton-block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster
+    if 512 <= Nr <= 16384 or (16384 < Nr <= 131072 and B * Nq > 32768):
+        # Morton-block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster; above 16384
+        # reference points a two-level index (radix-sorted build, super-blocks of 32 blocks)
         ws = torch.empty(int(L.ssf_knn_blocks_workspace_floats(B, Nr)), dtype=torch.float32, device=unknown.device)
         nat.check(L.ssf_knn_blocks_build(nat.ptr(known), B, Nr, nat.ptr(ws), nat.stream()))
         nat.check(L.ssf_knn_blocks_search(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(ws), B, Nq, Nr, nat.ptr(dist),

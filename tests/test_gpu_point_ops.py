@@ -175,7 +175,9 @@ def test_scatter(L, C, n):
 
 
 @pytest.mark.parametrize("B,Nq,Nr,k,dup,off", [(2, 700, 1000, 16, False, False), (2, 2048, 8192, 16, True, True), (1, 8192, 8192, 7, True, False),
-                                               (3, 513, 2048, 3, False, True), (1, 300, 16384, 5, False, False), (2, 64, 33, 16, False, False)])
+                                               (3, 513, 2048, 3, False, True), (1, 300, 16384, 5, False, False), (2, 64, 33, 16, False, False),
+                                               (1, 4096, 16385, 16, True, False), (2, 3000, 40000, 16, True, True), (1, 2048, 65536, 7, False, False),
+                                               (1, 1024, 100001, 16, True, False), (1, 512, 131072, 3, False, True)])
 def test_knn_blocks_equals_brute_force(B, Nq, Nr, k, dup, off):
     """The Morton-block search returns exactly the brute-force scan's indices and distances (ties included)."""
     import torch
@@ -183,7 +185,7 @@ def test_knn_blocks_equals_brute_force(B, Nq, Nr, k, dup, off):
     g = torch.Generator().manual_seed(Nq + Nr + k)
     ref = torch.randn(B, Nr, 3, generator=g) * torch.tensor([30.0, 20.0, 2.0])
     if dup:  # duplicated points: exact distance ties, the index order is observable
-        ref[:, Nr // 2:] = ref[:, :Nr - Nr // 2]
+        ref[:, Nr // 2:] = ref[:, :Nr - Nr // 2].clone()
     query = ref[:, torch.randperm(Nr, generator=g)[:Nq] % Nr].clone() if Nq <= Nr else torch.randn(B, Nq, 3, generator=g) * 20
     query[:, ::3] += torch.randn(B, (Nq + 2) // 3, 3, generator=g)
     qadd = (torch.randn(B, Nq, 3, generator=g) * 0.5).cuda() if off else None

@@ -44,6 +44,10 @@ int ssf_dense_tc(const ssf_dense_args* args, void* stream);
  * SM).  mode 0: never; 1 (default): where it measured faster (pooled plain-row layers); 2: every eligible layer.  Results are
  * bit-identical across modes.  Returns the previous mode. */
 int ssf_dense_set_variant(int mode);
+/* Plain-row inputs and stored outputs travel by tensor-map TMA (cp.async.bulk.tensor, 32 x 32 fp32 boxes, 128-byte swizzle) when the
+ * arrays are 16-byte aligned with leading dimensions that are multiples of 4 floats; 0 switches those paths off (cp.async / st.global
+ * instead).  Results are bit-identical either way.  Returns the previous setting. */
+int ssf_dense_set_tma(int on);
 int ssf_dense_args_bytes(void);   /* sizeof(ssf_dense_args) as compiled, for binding self-checks */
 #ifdef __cplusplus
 }

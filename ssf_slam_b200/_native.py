@@ -54,6 +54,7 @@ SIGNATURES = {
     "ssf_dense_tc": ("pp", _I),
     "ssf_dense_args_bytes": ("", _I),
     "ssf_dense_set_variant": ("i", _I),
+    "ssf_dense_set_tma": ("i", _I),
     "ssf_frontend": ("ppiiippQpifpppp", _I),
     "ssf_solve_rt_f64": ("ppiippp", _I),
     "ssf_gmm_mask": ("ppiiidppp", _I),

@@ -23,6 +23,8 @@
 // The accumulator is double buffered in TMEM when 2 N + 256 <= 512 columns, so the epilogue of one tile overlaps the
 // MMAs of the next.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled signature (types only: the entry point is fetched through cudart)
 #include "tc_common.cuh"
 #include "ssf_dense.h"
 
@@ -47,7 +49,19 @@ constexpr int W_SMEM_MAX = 150 * 1024;    // bytes of shared memory for weight i
 constexpr int LIGHT_SMEM_MAX = 112 * 1024; // per-CTA shared memory of the light variant (two CTAs per SM)
 constexpr int STG_LD = KC + 4;            // row stride (floats) of a producer warp's transpose tile
 
+// Tensor maps (TMA descriptors) of the plain-row inputs and of the stored output: 2-D fp32 tensors [rows, channels] with
+// 32 x 32 boxes and the 128-byte swizzle, encoded on the host per launch and handed to the kernel as a __grid_constant__
+// parameter.  A producer warp then fetches its 32 rows x 32 channels of a K chunk with ONE cp.async.bulk.tensor issued by one
+// lane (rows beyond the tensor are zero-filled by the TMA engine), and a STORE-epilogue warp writes its 32 x 32 output box
+// with one cp.async.bulk.tensor store (rows beyond the tensor are clipped) -- instead of 8 address computations + 8 cp.async,
+// resp. 8 shared-memory loads + 8 predicated global stores, per lane.
+struct alignas(64) DenseMaps {
+    CUtensorMap x1, x2, y;
+};
+
 struct DenseCfg {
+    int tma_a;       // plain-row A operand fetched by tensor-map TMA
+    int tma_y;       // STORE epilogue written by tensor-map TMA
     int Nt;          // columns of a CTA tile
     int nk;          // K chunks
     int nstage;      // weight stages in shared memory
@@ -67,6 +81,25 @@ __device__ __forceinline__ void cp_async16_ca(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ssf_smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// ---- tensor-map TMA (SASS: UTMALDG / UTMASTG).  Boxes are 32 rows x 128 bytes with CU_TENSOR_MAP_SWIZZLE_128B: the 16-byte
+// chunk j of box row r sits at r * 128 + ((j ^ (r & 7)) << 4) of the 1024-byte aligned tile, so thread = row accesses are
+// bank-conflict free without padding.
+constexpr int TMA_TILE_BYTES = 32 * 128;
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c_inner, int c_row, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     ssf_smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_row), "r"(ssf_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c_inner, int c_row, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(ssf_smem_u32(src_smem)), "r"(c_inner), "r"(c_row)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tma_swz(int row, int chunk16) { return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4)); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -111,7 +144,7 @@ struct RowCtx {
 //                    half of the columns.
 template <int VARIANT>
 __global__ void __launch_bounds__(VARIANT == 1 ? DT_THREADS_LIGHT : (VARIANT == 3 ? DT_THREADS_FULL : DT_THREADS), VARIANT == 1 ? 2 : 1)
-dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
+dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMaps maps) {
     constexpr int NPROD = (VARIANT == 0 || VARIANT == 3) ? 2 : 1;   // producer warpgroups
     constexpr int NEPI = VARIANT >= 2 ? 2 : 1;                      // epilogue warpgroups
     constexpr int SPW = VARIANT == 2 ? 4 : 2;                       // A stages per producer warpgroup
@@ -138,8 +171,14 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
     uint64_t* d_full = bars + 40;                   // [2]
     uint64_t* d_empty = bars + 42;                  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
-    float* sStage = reinterpret_cast<float*>(bars + 46);   // [4 NPROD producer warps][pd + 1 slots][32 rows][STG_LD]
+    uint64_t* a_tma = bars + 46;                    // [8 producer warps][4 slots]: completion of the tensor-map loads
+    float* sStage = reinterpret_cast<float*>(bars + 78);   // [4 NPROD producer warps][pd + 1 slots][32 rows][STG_LD]
     float* sEpi = sStage + 4 * NPROD * (cfg.pd + 1) * (32 * STG_LD);   // [4 NEPI epilogue warps][32 rows][STG_LD]  (STORE epilogue)
+    // tensor-map tiles: 4 KB each, 1024-byte aligned, carved out of the SAME regions as the padded tiles they replace (those
+    // are 4.5 KB each, so the aligned 4 KB tiles of the same count (>= 4) always fit, and a kernel that uses the tensor-map
+    // path for only one of the two roles never has the other role's padded tiles in the way)
+    uint8_t* sTmaA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sStage) + 1023) & ~static_cast<uintptr_t>(1023));   // [producer warp][slot]
+    uint8_t* sTmaE = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sEpi) + 1023) & ~static_cast<uintptr_t>(1023));     // [epilogue warp]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == W_MMA) tc_alloc(tmem_slot, TCOLS);
@@ -156,6 +195,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             ssf_mbar_init(&d_full[i], 1);
             ssf_mbar_init(&d_empty[i], 128 * NEPI);
         }
+        for (int i = 0; i < 32; ++i) ssf_mbar_init(&a_tma[i], 1);
         ssf_mbar_fence_init();
     }
     for (int i = tid; i < a.K; i += NTHR) {
@@ -298,7 +338,30 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
         int pf_n = 0, pf_t = 0, pf_kc = 0;
         int my_pf = my_of(0, load_idx(wg));
         int idx_nx = load_idx(wg + NPROD);
+        const bool tma_a = cfg.tma_a != 0;
+        uint8_t* ttile = sTmaA + (size_t)warp * D * TMA_TILE_BYTES;     // this warp's ring of tensor-map tiles
+        uint64_t* tbar = a_tma + warp * 4;
         auto issue_next = [&]() {   // cp.async of the next chunk of the sequence (if any) + one commit group, always
+            if (tma_a) {
+                // one elected lane fetches the warp's 32 rows x 32 channels box; rows past the end are zero-filled
+                if (pf_n < total_n) {
+                    const int k0 = pf_kc * KC;
+                    const int it_pf = wg + pf_t * NPROD;
+                    const int row0 = (int)(((long long)blockIdx.x + (long long)it_pf * gridDim.x) * 128 + (warp & 3) * 32);
+                    if (lane == 0) {
+                        const int slot = pf_n % D;
+                        ssf_mbar_expect_tx(&tbar[slot], TMA_TILE_BYTES);
+                        if (k0 < a.c1) tma_load_2d(ttile + slot * TMA_TILE_BYTES, &maps.x1, k0, row0, &tbar[slot]);
+                        else tma_load_2d(ttile + slot * TMA_TILE_BYTES, &maps.x2, k0 - a.c1, row0, &tbar[slot]);
+                    }
+                    if (++pf_kc == nk) {
+                        pf_kc = 0;
+                        ++pf_t;
+                    }
+                }
+                ++pf_n;
+                return;
+            }
             if (pf_n < total_n) {
                 const int k0 = pf_kc * KC;
                 const float* base;
@@ -328,6 +391,19 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             cp_async_commit();
         };
         auto take_chunk = [&](int n, float (&v)[4][8]) {   // waits for chunk n of the sequence, reads this thread's row
+            if (tma_a) {
+                const int slot = n % D;
+                ssf_mbar_wait(&tbar[slot], (uint32_t)((n / D) & 1));
+                const uint8_t* src = ttile + slot * TMA_TILE_BYTES;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 x = *reinterpret_cast<const float4*>(src + tma_swz(lane, 2 * q));
+                    const float4 y = *reinterpret_cast<const float4*>(src + tma_swz(lane, 2 * q + 1));
+                    v[q][0] = x.x; v[q][1] = x.y; v[q][2] = x.z; v[q][3] = x.w; v[q][4] = y.x; v[q][5] = y.y; v[q][6] = y.z; v[q][7] = y.w;
+                }
+                __syncwarp();   // the slot is refilled by the tensor-map load issued for chunk n + D in the next step
+                return;
+            }
             if (PD == 1) cp_async_wait<1>();
             else cp_async_wait<2>();
             __syncwarp();
@@ -489,6 +565,32 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
                 float* et = sEpi + (warp - W_EPI) * (32 * STG_LD);
                 const int rg = lane >> 3, pc = lane & 7;
                 const long long row0 = row - lane;     // first row of this warp's 32
+                if (cfg.tma_y) {
+                    // tensor-map store: the warp's 32 x 32 box is written swizzled into its 4 KB tile and leaves with one
+                    // cp.async.bulk.tensor issued by one lane (rows past the end are clipped by the TMA engine)
+                    uint8_t* tt = sTmaE + (size_t)(warp - W_EPI) * TMA_TILE_BYTES;
+                    for (int c = c_lo; c < c_hi; c += 32) {
+                        float va[16], vb[16];
+                        tc_ld16(t_d + c, va);
+                        tc_ld16(t_d + c + 16, vb);
+                        tc_ld_wait();
+                        finish16(c, va);
+                        finish16(c + 16, vb);
+                        if (lane == 0) tma_store_wait_read();   // the previous box has been read out of the tile
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            *reinterpret_cast<float4*>(tt + tma_swz(lane, q)) = make_float4(va[q * 4], va[q * 4 + 1], va[q * 4 + 2], va[q * 4 + 3]);
+                            *reinterpret_cast<float4*>(tt + tma_swz(lane, 4 + q)) = make_float4(vb[q * 4], vb[q * 4 + 1], vb[q * 4 + 2], vb[q * 4 + 3]);
+                        }
+                        fence_proxy_async_smem();   // generic-proxy writes -> visible to the async proxy (TMA)
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&maps.y, n0 + c, (int)row0, tt);
+                            tma_store_commit();
+                        }
+                    }
+                } else
                 for (int c = c_lo; c < c_hi; c += 32) {
                     float va[16], vb[16];
                     DTRACE(1, 3);   // previous iteration's tail
@@ -566,12 +668,56 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg) {
             DTRACE(1, 15);
         }
     }
+    if (cfg.tma_y && lane == 0) tma_store_wait_all();   // (no-op for threads that issued no bulk store)
     tc_fence_before();
     __syncthreads();
     if (warp == W_MMA) tc_dealloc(tmem, TCOLS);
 }
 
 }  // namespace
+
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
+typedef CUresult (*ssf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ssf_encode_tiled_fn encode_tiled_fn() {
+    static ssf_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<ssf_encode_tiled_fn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+// fp32 [rows, cols] row-major with leading dimension ld (floats): 32 x 32 boxes, 128-byte swizzle, zero fill / clipping out of bounds
+static bool encode_rows_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld) {
+    ssf_encode_tiled_fn fn = encode_tiled_fn();
+    if (fn == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || ld % 4 != 0 || cols % 32 != 0 || rows <= 0 || rows > 0x7fffffffLL) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_dense_tma = -1;   // tensor-map TMA paths: 1 on (default), 0 off (SSF_DENSE_TMA=0: measurement / regression switch)
+static int dense_tma() {
+    if (g_dense_tma < 0) {
+        const char* e = getenv("SSF_DENSE_TMA");
+        g_dense_tma = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_dense_tma;
+}
+
+extern "C" int ssf_dense_set_tma(int on) {
+    const int prev = dense_tma();
+    g_dense_tma = on ? 1 : 0;
+    return prev;
+}
 
 static int g_dense_variant = -1;   // 0: heavy variant everywhere, 1: light variant where it pays (default), 2: wherever eligible
 static int dense_variant() {
@@ -622,7 +768,7 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     cfg.nstage = cfg.resident ? cfg.nk : (int)(W_SMEM_MAX / wchunk);
     if (cfg.nstage > 16) cfg.nstage = 16;
     cfg.n_tiles = (int)((a.rows + 127) / 128);
-    const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
+    const size_t smem_fixed = (size_t)cfg.nstage * wchunk + (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 80 * 8;
     const size_t tile_b = (size_t)32 * STG_LD * 4;   // one staging tile of a warp
     const int light_mode = dense_variant();
     // light_mode 1: only where it measured faster (pooled plain-row layers: the epilogue warps are the bottleneck and the
@@ -656,7 +802,7 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     const bool full = full_r || (light_mode && !light && !wide && a.a_mode == 1 && a.H == nullptr && full_ok);
     const int n_pw = (light || wide) ? 4 : 8, n_ew = (wide || full) ? 8 : 4;
     const size_t smem_cap = light ? (size_t)LIGHT_SMEM_MAX : (size_t)227 * 1024;
-    const size_t smem_par = (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 48 * 8;
+    const size_t smem_par = (size_t)(4 * a.K + 5 * cfg.Nt) * 4 + 80 * 8;
     size_t w_budget = smem_cap - smem_par - ((size_t)n_pw * 2 + n_ew) * tile_b;
     if (w_budget > (size_t)W_SMEM_MAX) w_budget = W_SMEM_MAX;
     cfg.resident = (size_t)cfg.nk * wchunk <= w_budget;
@@ -667,10 +813,19 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     cfg.pd = 2;
     while (cfg.pd > 1 && smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b > smem_cap) --cfg.pd;
     const size_t smem = smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b;
-    if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem, (cudaStream_t)stream>>>(a, cfg);
-    else if (full) dense_tc_kernel<3><<<grid, DT_THREADS_FULL, smem, (cudaStream_t)stream>>>(a, cfg);
-    else if (wide) dense_tc_kernel<2><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
-    else dense_tc_kernel<0><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg);
+    DenseMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    cfg.tma_a = cfg.tma_y = 0;
+    if (dense_tma()) {
+        if (a.a_mode == 0 && encode_rows_map(&maps.x1, a.x1, a.rows, a.c1, a.ld1) &&
+            (a.x2 == nullptr || encode_rows_map(&maps.x2, a.x2, a.rows, a.c2, a.ld2)))
+            cfg.tma_a = 1;
+        if (a.epi_mode == SSF_EPI_STORE && encode_rows_map(&maps.y, a.y, a.rows, a.N, a.ldy)) cfg.tma_y = 1;
+    }
+    if (light) dense_tc_kernel<1><<<grid, DT_THREADS_LIGHT, smem, (cudaStream_t)stream>>>(a, cfg, maps);
+    else if (full) dense_tc_kernel<3><<<grid, DT_THREADS_FULL, smem, (cudaStream_t)stream>>>(a, cfg, maps);
+    else if (wide) dense_tc_kernel<2><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg, maps);
+    else dense_tc_kernel<0><<<grid, DT_THREADS, smem, (cudaStream_t)stream>>>(a, cfg, maps);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

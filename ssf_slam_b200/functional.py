@@ -49,6 +49,12 @@ def set_dense_variant(mode):
     return int(nat.lib().ssf_dense_set_variant(int(mode)))
 
 
+def set_dense_tma(on):
+    """Tensor-map TMA paths of ``dense_tc`` (plain-row A operand, STORE epilogue) on / off; returns the previous setting.  Results
+    are bit-identical either way."""
+    return int(nat.lib().ssf_dense_set_tma(1 if on else 0))
+
+
 def dense_tc(wimg, N, K, *, x1=None, x2=None, G=None, offG=0, H=None, offH=0, b1=None, Wd1=None, act1=ACT_NONE, idx=None,
              pos_src=None, pos_q=None, bias=None, Hq=None, Wd2=None, act=ACT_NONE, epi=EPI_STORE, wvec=None, b0=0.0, S=0):
     """Tensor-core dense layer (csrc/dense_tc.cu, include/ssf_dense.h).  Rows: plain ``x1 | x2`` ([..., c]) or the grouped

@@ -222,3 +222,37 @@ def test_dense_tc_full_variant_grouped_without_point_block():
     A = _act(G[bi, li].double() + b1.double() + dirs @ Wd1.double(), 1)
     ref = _act(A @ W.double().t() + bias.double(), 1).max(dim=2).values
     assert float((y1.cpu().double() - ref).abs().max()) < 3e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("rows,K,N,two_seg,epi", [(128, 32, 32, False, 0), (1000, 96, 128, True, 0), (300, 512, 256, True, 0), (257, 64, 64, False, 0),
+                                                  (148 * 128 * 3 + 130, 96, 128, True, 0), (148 * 128 * 2 + 5, 256, 256, False, 0),
+                                                  (148 * 128 * 2 + 37, 64, 64, False, 0), (4096 * 16, 64, 128, False, 1), (33, 64, 64, False, 0)])
+def test_dense_tc_tensor_map_tma_is_bit_identical(rows, K, N, two_seg, epi):
+    """The tensor-map TMA paths (cp.async.bulk.tensor loads of the plain-row A operand with zero fill past the last row, bulk
+    tensor stores of the STORE epilogue with clipping) against the cp.async / st.global paths: bit-identical, ragged row counts and
+    two-segment inputs included; and against the fp64 product."""
+    from ssf_slam_b200 import functional as F_, tc
+    g = torch.Generator().manual_seed(7 * rows + K + N)
+    X = torch.randn(rows, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    img = tc.dense_image(W).cuda()
+    kw = dict(bias=b.cuda(), act=2, epi=epi, S=16 if epi == 1 else 0)
+    if two_seg:
+        c1 = 64 if K > 64 else 32
+        xs = dict(x1=X[:, :c1].contiguous().cuda(), x2=X[:, c1:].contiguous().cuda())
+    else:
+        xs = dict(x1=X.cuda())
+    outs = {}
+    prev = F_.set_dense_tma(True)
+    try:
+        for on in (True, False):
+            F_.set_dense_tma(on)
+            outs[on] = F_.dense_tc(img, N, K, **xs, **kw).cpu()
+    finally:
+        F_.set_dense_tma(prev)
+    assert torch.equal(outs[True], outs[False])
+    ref = _act(X.double() @ W.double().t() + b.double(), 2)
+    if epi == 1:
+        ref = ref.view(rows // 16, 16, N).max(dim=1)[0]
+    assert float((outs[True].double() - ref).abs().max()) < (3e-6 if K <= 256 else 6e-6) * max(1.0, float(ref.abs().max()))

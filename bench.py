@@ -320,11 +320,12 @@ def run_stress(args, rank, world, local):
     def step(x):
         fps = pu.furthest_point_sample(x, 2048)
         cent = pu.gather_operation(x.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
-        _, idx = pu.knn(16, x, x)
+        index = pu.build_index(x)            # one spatial index per cloud, shared by the kNN and the eight ball queries
+        _, idx = pu.knn(16, x, x, index=index)
         out = [idx]
         for ns in (16, 32):
             for r in (0.5, 1.0, 2.0, 4.0):
-                out.append(pu.ball_query(r, ns, x, cent))
+                out.append(pu.ball_query(r, ns, x, cent, index=index))
         return fps, out
 
     for _ in range(max(args.warmup, 1)):
@@ -361,6 +362,11 @@ def run_stress(args, rank, world, local):
     cent = pu.gather_operation(xyz.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2).contiguous()
     t = _timed(lambda: pu.furthest_point_sample(xyz, 2048), reps=3, warm=1)
     res["fps_npoint2048"] = {"ms": t * 1e3, "G_point_updates_per_s": B * N * 2048.0 / t / 1e9}
+    t = _timed(lambda: pu.build_index(xyz), reps=3, warm=1)
+    res["build_index"] = {"ms": t * 1e3}
+    index = pu.build_index(xyz)
+    t = _timed(lambda: pu.knn(16, xyz, xyz, index=index), reps=3, warm=1)
+    res["knn_k16_NxN_indexed"] = {"ms": t * 1e3, "G_pair_evals_per_s_bruteforce_equivalent": B * float(N) * N / t / 1e9}
     t = _timed(lambda: pu.knn(16, xyz, xyz), reps=3, warm=1)
     res["knn_k16_NxN"] = {"ms": t * 1e3, "G_pair_evals_per_s_bruteforce_equivalent": B * float(N) * N / t / 1e9,
                           "GB_per_s_compulsory": B * (24.0 * N + 4.0 * N * 16) / t / 1e9}
@@ -368,9 +374,10 @@ def run_stress(args, rank, world, local):
     res["knn_k16_2048xN"] = {"ms": t * 1e3, "G_pair_evals_per_s": B * 2048.0 * N / t / 1e9}
     for ns in (16, 32):
         for r in (0.5, 1.0, 2.0, 4.0):
-            t = _timed(lambda: pu.ball_query(r, ns, xyz, cent), reps=3, warm=1)
-            _, cnt = pu.ball_query(r, ns, xyz, cent, return_count=True)
-            res["ball_query_r%g_ns%d" % (r, ns)] = {"ms": t * 1e3, "G_pair_evals_per_s": B * 2048.0 * N / t / 1e9,
+            t = _timed(lambda: pu.ball_query(r, ns, xyz, cent, index=index), reps=3, warm=1)
+            t0 = _timed(lambda: pu.ball_query(r, ns, xyz, cent, use_index=False), reps=3, warm=1)
+            _, cnt = pu.ball_query(r, ns, xyz, cent, return_count=True, index=index)
+            res["ball_query_r%g_ns%d" % (r, ns)] = {"ms": t * 1e3, "ms_scan": t0 * 1e3, "G_pair_evals_per_s_bruteforce_equivalent": B * 2048.0 * N / t / 1e9,
                                                   "mean_in_range": float(cnt.float().mean().item())}
     line = {"metric": metric_name(args), "value": world * B * args.steps / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -488,20 +495,30 @@ def main():
             flows, _ = net.forward_pm(item[0], item[1])
             mask, odom = mask_pose(item, flows[0], masker or args.masker)
         keep.append((mask, odom))
-        if gatherer is not None and stream is not None:
-            gatherer.push(odom, mask, stream)   # this batch's poses + masks to every rank, on the gather stream, off the critical path
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_all(keep, main_st):
+        """The job's only communication: every rank's poses + masks of all its batches to every rank, ONE packed
+        all_gather_into_tensor on the gather stream once the batches are done (once per sequence, off the critical
+        streams).  Per-batch gathers were measured and rejected: NCCL's CTAs busy-wait for the peer while holding SM resources
+        the persistent tensor kernels need (2 GPUs: 97.4 % instead of 99 % weak-scaling efficiency)."""
+        for st in streams:
+            main_st.wait_stream(st)
+        odom = torch.stack([o for _, o in keep])
+        mask = torch.stack([m for m, _ in keep])
+        gatherer.push(odom, mask, main_st)
+        return gatherer.finish(main_st)
+
     def timed_device_leg(masker):
         keep = []
         for s in range(Wm):
-            device_step(s, keep, streams[s % NS], masker)     # warm-up includes the gather (NCCL channels, buffers)
+            device_step(s, keep, streams[s % NS], masker)
         if gatherer is not None:
-            gatherer.finish()
+            gather_all(keep, torch.cuda.current_stream(dev))   # warm-up includes the gather (NCCL channels, buffers)
         sync_all()
         if gatherer is not None:
             gatherer.gather_ms()
@@ -518,7 +535,7 @@ def main():
         for st in streams:
             main_st.wait_stream(st)
         if gatherer is not None:
-            gatherer.finish(main_st)    # the job is done when every rank holds every pose and mask
+            gather_all(keep, main_st)   # the job is done when every rank holds every pose and mask
         ev1.record(main_st)
         sync_all()
         launches = nat.launch_count() - l0
@@ -673,17 +690,16 @@ def main():
             "config": {"workload": workload_name(args), "masker": args.masker,
                        "pairs_per_step_per_gpu": B, "distinct_pairs": POOL, "distinct_batches": n_distinct,
                        "batching": "step s = frame pairs [s*B, s*B+B) mod %d of the rank's 200-frame sequence (sliding window)" % POOL,
-                       "sharding": "sequence id %% world (config 3), no collective on the hot path; every batch's poses+masks are "
-                                   "all-gathered by one packed all_gather_into_tensor on a side stream",
+                       "sharding": "sequence id %% world (config 3), no collective on the hot path; the job's poses+masks are "
+                                   "all-gathered once, by one packed all_gather_into_tensor on a side stream, inside the timed window",
                        "pipelining": "independent batches alternate over %d CUDA streams (per-stream pinned staging in the e2e leg)" % NS,
                        "l2": "per-step working set (~%.1f GB of intermediates) exceeds the 126 MB L2" % (B * 0.12 * N / 8192.0)},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": fe.h2d_bytes(B, N, seg=seg), "d2h_bytes_per_step": fe.d2h_bytes(B, N),
                     "ms_per_step": ems / K},
-            "gather": {"ms_total_on_side_stream": gather_ms, "collectives": K if world > 1 else 0,
-                       "bytes_per_rank_per_collective": B * (N + 56),
-                       "note": "max over ranks of the summed CUDA-event durations of the per-batch gathers (NCCL, own stream, overlapped "
-                               "with the next batches; inside the timed window only as far as the last one trails the compute)"},
+            "gather": {"ms": gather_ms, "collectives": 1 if world > 1 else 0, "bytes_per_rank": K * B * (N + 56),
+                       "note": "max over ranks of the CUDA-event duration of the one packed all_gather_into_tensor (NCCL, own stream, "
+                               "warmed in the warm-up); it is inside the timed window"},
             "latency": None if latency_ms is None else {"pairs": 1, "ms_per_pair": latency_ms, "note": "SceneFlowFrontEnd.process on one "
                         "host-resident frame pair (H2D + %s + D2H), mean of 20" % ("CUDA-graph replay" if args.graph else "eager launches")},
             "other_masker": None if other_ms is None else {"masker": other, "value": world * B * K / (other_ms * 1e-3), "ms_per_step": other_ms / K,

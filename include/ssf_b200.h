@@ -54,6 +54,11 @@ int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, void* strea
 int ssf_knn_blocks_search(int k, const float* query, const float* query_add, const float* ws, int B, int Nq, int Nr,
                           float* dist, int* idx, void* stream);
 
+/* ball_query through the index `ws` built by ssf_knn_blocks_build for the cloud xyz[B,N,3]: identical output to ssf_ball_query
+ * (ASF/SetCover.py:39-63 semantics), visiting only the blocks whose box can reach the ball.  nsample <= 32. */
+int ssf_ball_query_blocks(float radius, int nsample, const float* new_xyz, const float* ws, int B, int N, int S, int* idx, int* cnt,
+                          void* stream);
+
 /* Same result by a brute-force scan with one warp per two queries (lane = reference point): for the few-queries / large-cloud
  * corner (B * Nq <= 32768 and Nr > 16384, e.g. 2048 centres in 65536 points) where one thread per query leaves the GPU empty */
 int ssf_knn_warp_scan(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "ssf_knn_blocks_build": ("piipp", _I),
     "ssf_knn_blocks_search": ("ipppiiippp", _I),
     "ssf_knn_warp_scan": ("ipppiiippp", _I),
+    "ssf_ball_query_blocks": ("fippiiippp", _I),
     "ssf_three_nn": ("ppiiippp", _I),
     "ssf_ball_query": ("fippiiippp", _I),
     "ssf_grouping_operation": ("ppiiiiipp", _I),

@@ -689,6 +689,97 @@ __global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search2_kernel(int
     }
 }
 
+
+// Ball query through the same spatial index (either level count): blocks whose box bound exceeds r^2 cannot hold a point in
+// range (the bound is computed with the distance's own rounded operations and is monotone, see the header), every other block
+// is evaluated lane = point.  The reference semantics want the FIRST nsample hits in ascending INDEX order (ASF/SetCover.py:
+// 39-63), while the blocks come in Morton order: the warp keeps the nsample smallest hit indices in a lane-distributed sorted
+// list (the kNN list with the index as the key) and counts every hit.  Same output as ssf_ball_query, bit for bit.
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(KB_SEARCH_T, 12) ball_query_blocks_kernel(float r2, int nsample, const float* __restrict__ query,
+                                                                           const float* __restrict__ ws, long long ws_per_cloud, int S, int npad,
+                                                                           int nblk, int nsb, int* __restrict__ idx, int* __restrict__ cnt) {
+    extern __shared__ __align__(16) float4 sbox[];   // one level: [nblk] lo | [nblk] hi;  two levels: the super-block boxes
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const float* wsb = ws + (size_t)b * ws_per_cloud;
+    const float4* P = reinterpret_cast<const float4*>(wsb);
+    const float4* BLO = P + npad;
+    const float4* BHI = BLO + nblk;
+    const int nbox = TWO_LEVEL ? nsb : nblk;
+    {
+        const float4* src = TWO_LEVEL ? BHI + nblk : BLO;
+        for (int i = tid; i < 2 * nbox; i += KB_SEARCH_T) sbox[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    auto box_bound = [](const float4 lo, const float4 hi, float qx, float qy, float qz) -> float {
+        const float gx = fmaxf(0.f, fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)));
+        const float gy = fmaxf(0.f, fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)));
+        const float gz = fmaxf(0.f, fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)));
+        return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+    };
+    const int q_end = min(S, (int)(blockIdx.x + 1) * KB_QPB);
+    for (int qi = blockIdx.x * KB_QPB + warp; qi < q_end; qi += KB_SEARCH_T / 32) {
+        const float* qp = query + ((size_t)b * S + qi) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        unsigned list_i = 0xffffffffu, kth = 0xffffffffu;   // lane j = j-th smallest hit index so far; kth = the nsample-th
+        int total = 0;
+        auto visit = [&](int blk) {
+            const float4 p = __ldg(P + (size_t)blk * 32 + lane);
+            const bool hit = ssf_sqdist(qx, qy, qz, p.x, p.y, p.z) <= r2;   // padding points sit at +inf: never in range
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            total += __popc(mask);
+            const unsigned mine = (unsigned)__float_as_int(p.w);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const unsigned ci = __shfl_sync(0xffffffffu, mine, src);
+                if (ci >= kth) continue;   // warp-uniform
+                const int pos = __popc(__ballot_sync(0xffffffffu, list_i < ci));
+                const unsigned up = __shfl_up_sync(0xffffffffu, list_i, 1);
+                list_i = lane == pos ? ci : (lane > pos ? up : list_i);
+                kth = __shfl_sync(0xffffffffu, list_i, nsample - 1);
+            }
+        };
+        if (TWO_LEVEL) {
+            for (int g0 = 0; g0 < nsb; g0 += 32) {
+                const int sb = g0 + lane;
+                const bool near = sb < nsb && box_bound(sbox[sb], sbox[nsb + sb], qx, qy, qz) <= r2;
+                unsigned sm = __ballot_sync(0xffffffffu, near);
+                while (sm) {
+                    const int sl = __ffs(sm) - 1;
+                    sm &= sm - 1;
+                    const int blk = (g0 + sl) * 32 + lane;
+                    const bool bn = blk < nblk && box_bound(__ldg(BLO + blk), __ldg(BHI + blk), qx, qy, qz) <= r2;
+                    unsigned bm = __ballot_sync(0xffffffffu, bn);
+                    while (bm) {
+                        const int bl = __ffs(bm) - 1;
+                        bm &= bm - 1;
+                        visit((g0 + sl) * 32 + bl);
+                    }
+                }
+            }
+        } else {
+            for (int g0 = 0; g0 < nblk; g0 += 32) {
+                const int blk = g0 + lane;
+                const bool bn = blk < nblk && box_bound(sbox[blk], sbox[nblk + blk], qx, qy, qz) <= r2;
+                unsigned bm = __ballot_sync(0xffffffffu, bn);
+                while (bm) {
+                    const int bl = __ffs(bm) - 1;
+                    bm &= bm - 1;
+                    visit(g0 + bl);
+                }
+            }
+        }
+        const unsigned first = __shfl_sync(0xffffffffu, list_i, 0);
+        if (lane < nsample) {
+            const int v = total == 0 ? 0 : (int)(lane < total ? list_i : first);
+            idx[((size_t)b * S + qi) * nsample + lane] = v;
+        }
+        if (cnt != nullptr && lane == 0) cnt[(size_t)b * S + qi] = total;
+    }
+}
+
 inline int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -788,6 +879,26 @@ extern "C" int ssf_knn_warp_scan(int k, const float* query, const float* query_a
     if (k > Nr) return ssf_arg_error("knn: k exceeds the number of reference points");
     dim3 grid((Nq + 8 * KS_Q - 1) / (8 * KS_Q), B);
     knn_warp_scan_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, query, query_add, ref, Nq, Nr, dist, idx);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
+}
+
+// ball_query through the index built by ssf_knn_blocks_build for the same cloud (N points): same output as ssf_ball_query.
+// nsample <= 32 (the hit list is lane-distributed).
+extern "C" int ssf_ball_query_blocks(float radius, int nsample, const float* new_xyz, const float* ws, int B, int N, int S, int* idx,
+                                     int* cnt, void* stream) {
+    if (B <= 0 || S <= 0 || N <= 0) return ssf_arg_error("ball_query_blocks: empty input");
+    if (nsample <= 0 || nsample > 32) return ssf_arg_error("ball_query_blocks: nsample must be in [1,32]");
+    if (N > KB_MAX_REF) return ssf_arg_error("ball_query_blocks: at most 131072 points");
+    const float r2 = radius * radius;  // fp32 product, as the spec
+    const int npad = (N + 31) / 32 * 32, nblk = npad / 32, nsb = (nblk + 31) / 32;
+    dim3 grid((S + KB_QPB - 1) / KB_QPB, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > KB_ONE_LEVEL_MAX)
+        ball_query_blocks_kernel<true><<<grid, KB_SEARCH_T, (size_t)nsb * 32, st>>>(r2, nsample, new_xyz, ws, knn_ws_per_cloud(N), S, npad, nblk, nsb, idx, cnt);
+    else
+        ball_query_blocks_kernel<false><<<grid, KB_SEARCH_T, (size_t)nblk * 32, st>>>(r2, nsample, new_xyz, ws, knn_ws_per_cloud(N), S, npad, nblk, nsb, idx, cnt);
     ssf_count_launch();
     SSF_LAUNCH_CHECK();
     return SSF_OK;

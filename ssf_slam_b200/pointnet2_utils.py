@@ -50,10 +50,29 @@ def gather_operation(features, idx):
     return out
 
 
+INDEX_MAX_POINTS = 131072
+
+
 @torch.no_grad()
-def knn(k, unknown, known, offset=None):
+def build_index(xyz):
+    """Spatial index of the clouds xyz f32 [B,N,3] (N <= 131072) for ``knn(..., index=)`` and ``ball_query(..., index=)``:
+    Morton-sorted blocks of 32 points with bounding boxes (csrc/knn_blocks.cu).  Extension of the reference API: it lets
+    several searches in the same cloud (a radius sweep, kNN + ball query) share one build; every search returns exactly what
+    the un-indexed operator returns."""
+    nat.require_device()
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    L = nat.lib()
+    ws = torch.empty(int(L.ssf_knn_blocks_workspace_floats(B, N)), dtype=torch.float32, device=xyz.device)
+    nat.check(L.ssf_knn_blocks_build(nat.ptr(xyz), B, N, nat.ptr(ws), nat.stream()))
+    return ws
+
+
+@torch.no_grad()
+def knn(k, unknown, known, offset=None, index=None):
     """(k, query f32 [B,Nq,3], reference f32 [B,Nr,3]) -> (dist f32 [B,Nq,k] ascending, idx i32 [B,Nq,k]).
-    ``offset`` (extension): query is taken as unknown + offset without materialising the sum."""
+    ``offset`` (extension): query is taken as unknown + offset without materialising the sum.
+    ``index`` (extension): ``build_index(known)``, to share the build between calls."""
     nat.require_device()
     unknown, known = _f32(unknown), _f32(known)
     B, Nq, _ = unknown.shape
@@ -62,11 +81,10 @@ def knn(k, unknown, known, offset=None):
     idx = torch.empty(B, Nq, k, dtype=torch.int32, device=unknown.device)
     off = None if offset is None else _f32(offset)
     L = nat.lib()
-    if 512 <= Nr <= 16384 or (16384 < Nr <= 131072 and B * Nq > 32768):
+    if index is not None or 512 <= Nr <= 16384 or (16384 < Nr <= INDEX_MAX_POINTS and B * Nq > 32768):
         # Morton-block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster; above 16384
         # reference points a two-level index (radix-sorted build, super-blocks of 32 blocks)
-        ws = torch.empty(int(L.ssf_knn_blocks_workspace_floats(B, Nr)), dtype=torch.float32, device=unknown.device)
-        nat.check(L.ssf_knn_blocks_build(nat.ptr(known), B, Nr, nat.ptr(ws), nat.stream()))
+        ws = index if index is not None else build_index(known)
         nat.check(L.ssf_knn_blocks_search(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(ws), B, Nq, Nr, nat.ptr(dist),
                                           nat.ptr(idx), nat.stream()))
         return dist, idx
@@ -86,14 +104,23 @@ def three_nn(unknown, known):
 
 
 @torch.no_grad()
-def ball_query(radius, nsample, xyz, new_xyz, return_count=False):
-    """(radius, nsample, xyz f32 [B,N,3], new_xyz f32 [B,S,3]) -> idx i32 [B,S,nsample] (, cnt i32 [B,S])."""
+def ball_query(radius, nsample, xyz, new_xyz, return_count=False, index=None, use_index=None):
+    """(radius, nsample, xyz f32 [B,N,3], new_xyz f32 [B,S,3]) -> idx i32 [B,S,nsample] (, cnt i32 [B,S]).
+    Clouds of 2048 .. 131072 points are searched through the spatial index (``index`` = ``build_index(xyz)`` to share the build
+    between calls, e.g. a radius sweep); smaller ones, nsample > 32 or ``use_index=False`` by the brute-force scan.  Same output."""
     nat.require_device()
     xyz, new_xyz = _f32(xyz), _f32(new_xyz)
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     idx = torch.empty(B, S, nsample, dtype=torch.int32, device=xyz.device)
     cnt = torch.empty(B, S, dtype=torch.int32, device=xyz.device) if return_count else None   # without counts a query stops at nsample hits
+    if use_index is None:
+        use_index = index is not None or (2048 <= N <= INDEX_MAX_POINTS and 0 < nsample <= 32)
+    if use_index:
+        ws = index if index is not None else build_index(xyz)
+        nat.check(nat.lib().ssf_ball_query_blocks(float(radius), int(nsample), nat.ptr(new_xyz), nat.ptr(ws), B, N, S, nat.ptr(idx),
+                                                  nat.ptr(cnt), nat.stream()))
+        return (idx, cnt) if return_count else idx
     nat.check(nat.lib().ssf_ball_query(float(radius), int(nsample), nat.ptr(xyz), nat.ptr(new_xyz), B, N, S, nat.ptr(idx),
                                        nat.ptr(cnt), nat.stream()))
     return (idx, cnt) if return_count else idx

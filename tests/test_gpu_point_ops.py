@@ -115,11 +115,12 @@ def test_ball_query(pu, N, S, radius, nsample):
     new = xyz[:, :: max(1, N // S)][:, :S].copy()
     if radius < 0.01:
         new = new + 7.0  # nobody in range
-    bi, bc = pu.ball_query(radius, nsample, _cuda(xyz), _cuda(new), return_count=True)
     oi, oc = po.c_ball_query(radius, nsample, xyz, new)
-    assert np.array_equal(bc.cpu().numpy(), oc)
-    assert np.array_equal(bi.cpu().numpy(), oi)
-    assert np.array_equal(pu.ball_query(radius, nsample, _cuda(xyz), _cuda(new)).cpu().numpy(), oi)   # no counts: early exit
+    for use_index in (False, True) if N >= 64 else (False,):    # the brute-force scan and the spatial index: same output
+        bi, bc = pu.ball_query(radius, nsample, _cuda(xyz), _cuda(new), return_count=True, use_index=use_index)
+        assert np.array_equal(bc.cpu().numpy(), oc)
+        assert np.array_equal(bi.cpu().numpy(), oi)
+        assert np.array_equal(pu.ball_query(radius, nsample, _cuda(xyz), _cuda(new), use_index=use_index).cpu().numpy(), oi)   # no counts
 
 
 def test_ball_query_many_queries_thread_per_query_kernel(pu):
@@ -257,10 +258,18 @@ def test_config5_dense_stress_n65536(pu):
     fps = pu.furthest_point_sample(x, 2048)
     assert np.array_equal(fps.cpu().numpy(), po.c_fps(xyz, 2048))
     cent = np.ascontiguousarray(xyz[0][fps.cpu().numpy()[0].astype(np.int64)][None])
+    index = pu.build_index(x)                      # one build shared by the whole sweep (and by a kNN)
+    d2, i2 = pu.knn(16, _cuda(cent), x, index=index)
+    od2, oi2 = po.c_knn(16, cent, xyz)
+    assert np.array_equal(i2.cpu().numpy(), oi2) and np.array_equal(d2.cpu().numpy(), od2)
     for r in (0.5, 1.0, 2.0, 4.0):
-        bi, bc = pu.ball_query(r, 16, x, _cuda(cent), return_count=True)
         oi, oc = po.c_ball_query(r, 16, xyz, cent)
-        assert np.array_equal(bc.cpu().numpy(), oc) and np.array_equal(bi.cpu().numpy(), oi), r
+        for kw in (dict(index=index), dict(use_index=False)):
+            bi, bc = pu.ball_query(r, 16, x, _cuda(cent), return_count=True, **kw)
+            assert np.array_equal(bc.cpu().numpy(), oc) and np.array_equal(bi.cpu().numpy(), oi), (r, kw)
+    oi, oc = po.c_ball_query(30.0, 32, xyz, cent[:, :64])      # a ball that holds most of the cloud
+    bi, bc = pu.ball_query(30.0, 32, x, _cuda(cent[:, :64]), return_count=True, index=index)
+    assert np.array_equal(bc.cpu().numpy(), oc) and np.array_equal(bi.cpu().numpy(), oi)
 
 
 def test_error_behaviour_python_exceptions(pu):

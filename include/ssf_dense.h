@@ -45,8 +45,9 @@ int ssf_dense_tc(const ssf_dense_args* args, void* stream);
  * bit-identical across modes.  Returns the previous mode. */
 int ssf_dense_set_variant(int mode);
 /* Plain-row inputs and stored outputs travel by tensor-map TMA (cp.async.bulk.tensor, 32 x 32 fp32 boxes, 128-byte swizzle) when the
- * arrays are 16-byte aligned with leading dimensions that are multiples of 4 floats; 0 switches those paths off (cp.async / st.global
- * instead).  Results are bit-identical either way.  Returns the previous setting. */
+ * arrays are 16-byte aligned with leading dimensions that are multiples of 4 floats (level 1, default); 0 switches those paths off
+ * (cp.async / st.global instead); 2 also fetches the gathered rows of grouped layers by tile::gather4 (correct, measured slower than
+ * the cp.async gather, hence not the default).  Results are bit-identical at every level.  Returns the previous level. */
 int ssf_dense_set_tma(int on);
 int ssf_dense_args_bytes(void);   /* sizeof(ssf_dense_args) as compiled, for binding self-checks */
 #ifdef __cplusplus

@@ -19,8 +19,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (3 * 8 * 32))()
 L = nat.lib()
-L.ssf_cv_trace_read.argtypes = [ctypes.c_void_p]
-assert L.ssf_cv_trace_read(buf) == 0
+L.raw.ssf_cv_trace_read.argtypes = [ctypes.c_void_p]
+assert L.raw.ssf_cv_trace_read(buf) == 0
 t = np.array(buf[:]).reshape(3, 8, 32)
 t0 = t[0, 0, 0]
 names = ["start", "P done", "E1 wait", "E1 done", "bar", "ATT done", "E2 wait", "E2 done", "E3 wait", "E3 done", "E4 wait", "E4 done", "E5 wait", "E5 done"]

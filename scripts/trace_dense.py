@@ -6,7 +6,7 @@ import torch
 from ssf_slam_b200 import functional as F_, tc, _native as nat
 
 L = nat.lib()
-L.ssf_dense_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
+L.raw.ssf_dense_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
 buf = (ctypes.c_longlong * 48)()
 shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[1:] if not s.startswith("g")] or [(524288, 64, 64), (262144, 256, 256)]
 grouped = [a for a in sys.argv[1:] if a.startswith("g")]   # e.g. g8x8192x2048x64: B clouds, Nq query points, Nsrc source rows, K = N
@@ -17,10 +17,10 @@ for rows, K, N in shapes:
     for _ in range(2):
         F_.dense_tc(img, N, K, x1=X, bias=b, act=2)
     torch.cuda.synchronize()
-    L.ssf_dense_trace_read(buf, 1)
+    L.raw.ssf_dense_trace_read(buf, 1)
     F_.dense_tc(img, N, K, x1=X, bias=b, act=2)
     torch.cuda.synchronize()
-    L.ssf_dense_trace_read(buf, 1)
+    L.raw.ssf_dense_trace_read(buf, 1)
     t = list(buf)
     tiles = -(-((rows + 127) // 128) // 148)     # tiles of CTA 0
     chunks = tiles * (K // 32)
@@ -44,10 +44,10 @@ for spec in grouped:
     for _ in range(2):
         run()
     torch.cuda.synchronize()
-    L.ssf_dense_trace_read(buf, 1)
+    L.raw.ssf_dense_trace_read(buf, 1)
     run()
     torch.cuda.synchronize()
-    L.ssf_dense_trace_read(buf, 1)
+    L.raw.ssf_dense_trace_read(buf, 1)
     t = list(buf)
     tiles = -(-(B * Nq * 16 // 128) // 148)
     chunks = tiles * (K // 32)

@@ -124,6 +124,7 @@ def lib():
                                "ssf_slam_b200 has no CPU fallback" % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
         ns = _Lib()
+        ns.raw = L      # the ctypes handle itself (developer scripts reach trace-build symbols through it)
         for name, (codes, res) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = [_CODES[c] for c in codes]

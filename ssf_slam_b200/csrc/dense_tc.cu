@@ -57,11 +57,13 @@ constexpr int STG_LD = KC + 4;            // row stride (floats) of a producer w
 // resp. 8 shared-memory loads + 8 predicated global stores, per lane.
 struct alignas(64) DenseMaps {
     CUtensorMap x1, x2, y;
+    CUtensorMap g;   // grouped mode: the source rows G [B * Nsrc, ldG] with 32 x 1 boxes, fetched four rows at a time (tile::gather4)
 };
 
 struct DenseCfg {
     int tma_a;       // plain-row A operand fetched by tensor-map TMA
     int tma_y;       // STORE epilogue written by tensor-map TMA
+    int tma_g;       // grouped A operand: neighbour rows gathered by tensor-map TMA (tile::gather4)
     int Nt;          // columns of a CTA tile
     int nk;          // K chunks
     int nstage;      // weight stages in shared memory
@@ -89,6 +91,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                      ssf_smem_u32(dst_smem)),
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_row), "r"(ssf_smem_u32(bar))
+                 : "memory");
+}
+// four rows r0..r3 of a 2-D tensor (box = 32 channels x 1 row), 128 bytes each, land consecutively at dst (SASS: UTMALDG.2D.GATHER4)
+__device__ __forceinline__ void tma_gather4(void* dst_smem, const CUtensorMap* map, int c_inner, int r0, int r1, int r2, int r3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                     ssf_smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(ssf_smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c_inner, int c_row, const void* src_smem) {
@@ -338,10 +347,33 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
         int pf_n = 0, pf_t = 0, pf_kc = 0;
         int my_pf = my_of(0, load_idx(wg));
         int idx_nx = load_idx(wg + NPROD);
-        const bool tma_a = cfg.tma_a != 0;
+        const bool tma_g = cfg.tma_g != 0;
+        const bool tma_a = cfg.tma_a != 0 || tma_g;   // either way the chunk arrives in this warp's ring of swizzled tensor-map tiles
         uint8_t* ttile = sTmaA + (size_t)warp * D * TMA_TILE_BYTES;     // this warp's ring of tensor-map tiles
         uint64_t* tbar = a_tma + warp * 4;
         auto issue_next = [&]() {   // cp.async of the next chunk of the sequence (if any) + one commit group, always
+            if (tma_g) {
+                // gathered neighbour rows: lanes 0..7 each fetch four of the warp's 32 source rows (128 bytes of each) with one
+                // tile::gather4 -- no per-lane address arithmetic, no load-store-unit queue slots held while the rows travel
+                if (pf_n < total_n) {
+                    const int k0 = pf_kc * KC;
+                    const int slot = pf_n % D;
+                    const int g0 = (lane & 7) * 4;
+                    const int r0 = __shfl_sync(0xffffffffu, my_pf, g0), r1 = __shfl_sync(0xffffffffu, my_pf, g0 + 1);
+                    const int r2 = __shfl_sync(0xffffffffu, my_pf, g0 + 2), r3 = __shfl_sync(0xffffffffu, my_pf, g0 + 3);
+                    if (lane == 0) ssf_mbar_expect_tx(&tbar[slot], TMA_TILE_BYTES);
+                    __syncwarp();
+                    if (lane < 8) tma_gather4(ttile + slot * TMA_TILE_BYTES + lane * 512, &maps.g, a.offG + k0, r0, r1, r2, r3, &tbar[slot]);
+                    if (++pf_kc == nk) {
+                        pf_kc = 0;
+                        ++pf_t;
+                        my_pf = my_of(pf_t, idx_nx);
+                        idx_nx = load_idx(wg + (pf_t + 1) * NPROD);
+                    }
+                }
+                ++pf_n;
+                return;
+            }
             if (tma_a) {
                 // one elected lane fetches the warp's 32 rows x 32 channels box; rows past the end are zero-filled
                 if (pf_n < total_n) {
@@ -694,28 +726,32 @@ static ssf_encode_tiled_fn encode_tiled_fn() {
     return fn;
 }
 // fp32 [rows, cols] row-major with leading dimension ld (floats): 32 x 32 boxes, 128-byte swizzle, zero fill / clipping out of bounds
-static bool encode_rows_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld) {
+static bool encode_rows_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld, unsigned box_rows = 32) {
     ssf_encode_tiled_fn fn = encode_tiled_fn();
     if (fn == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || ld % 4 != 0 || cols % 32 != 0 || rows <= 0 || rows > 0x7fffffffLL) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {32, box_rows}, estr[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_dense_tma = -1;   // tensor-map TMA paths: 1 on (default), 0 off (SSF_DENSE_TMA=0: measurement / regression switch)
+// tensor-map TMA paths: 0 off, 1 (default) plain-row A operand + STORE epilogue, 2 also the grouped A operand by tile::gather4.
+// Level 2 is correct but measured SLOWER than the per-lane cp.async gather on B200 (su0, 16.7 M rows: 2.11 vs 1.86 ms: the
+// gathered rows are re-used by neighbouring queries and cp.async.ca keeps them in L1, the TMA engine goes to L2 every time), so it
+// is not the default.  SSF_DENSE_TMA=0/1/2 or ssf_dense_set_tma() select the level (measurement / regression switch).
+static int g_dense_tma = -1;
 static int dense_tma() {
     if (g_dense_tma < 0) {
         const char* e = getenv("SSF_DENSE_TMA");
-        g_dense_tma = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_dense_tma = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     }
     return g_dense_tma;
 }
 
 extern "C" int ssf_dense_set_tma(int on) {
     const int prev = dense_tma();
-    g_dense_tma = on ? 1 : 0;
+    g_dense_tma = on < 0 ? 0 : (on > 2 ? 2 : on);
     return prev;
 }
 
@@ -815,8 +851,11 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     const size_t smem = smem_w + ((size_t)n_pw * (cfg.pd + 1) + n_ew) * tile_b;
     DenseMaps maps;
     memset(&maps, 0, sizeof(maps));
-    cfg.tma_a = cfg.tma_y = 0;
+    cfg.tma_a = cfg.tma_y = cfg.tma_g = 0;
     if (dense_tma()) {
+        if (dense_tma() >= 2 && a.a_mode == 1 && a.Nq > 0 && a.Nsrc > 0 && a.ldG % 32 == 0 && a.offG % 4 == 0 &&
+            encode_rows_map(&maps.g, a.G, (a.rows / ((long long)a.S * a.Nq)) * a.Nsrc, a.ldG, a.ldG, 1))
+            cfg.tma_g = 1;
         if (a.a_mode == 0 && encode_rows_map(&maps.x1, a.x1, a.rows, a.c1, a.ld1) &&
             (a.x2 == nullptr || encode_rows_map(&maps.x2, a.x2, a.rows, a.c2, a.ld2)))
             cfg.tma_a = 1;

@@ -49,10 +49,10 @@ def set_dense_variant(mode):
     return int(nat.lib().ssf_dense_set_variant(int(mode)))
 
 
-def set_dense_tma(on):
-    """Tensor-map TMA paths of ``dense_tc`` (plain-row A operand, STORE epilogue) on / off; returns the previous setting.  Results
-    are bit-identical either way."""
-    return int(nat.lib().ssf_dense_set_tma(1 if on else 0))
+def set_dense_tma(level):
+    """Tensor-map TMA paths of ``dense_tc``: 0 off, 1 (default) plain-row A operand + STORE epilogue, 2 also the gathered rows of
+    grouped layers (tile::gather4; measured slower, kept for the record).  Returns the previous level; results are bit-identical."""
+    return int(nat.lib().ssf_dense_set_tma(int(level)))
 
 
 def dense_tc(wimg, N, K, *, x1=None, x2=None, G=None, offG=0, H=None, offH=0, b1=None, Wd1=None, act1=ACT_NONE, idx=None,

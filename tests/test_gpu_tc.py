@@ -244,10 +244,10 @@ def test_dense_tc_tensor_map_tma_is_bit_identical(rows, K, N, two_seg, epi):
     else:
         xs = dict(x1=X.cuda())
     outs = {}
-    prev = F_.set_dense_tma(True)
+    prev = F_.set_dense_tma(1)
     try:
         for on in (True, False):
-            F_.set_dense_tma(on)
+            F_.set_dense_tma(1 if on else 0)
             outs[on] = F_.dense_tc(img, N, K, **xs, **kw).cpu()
     finally:
         F_.set_dense_tma(prev)
@@ -256,3 +256,29 @@ def test_dense_tc_tensor_map_tma_is_bit_identical(rows, K, N, two_seg, epi):
     if epi == 1:
         ref = ref.view(rows // 16, 16, N).max(dim=1)[0]
     assert float((outs[True].double() - ref).abs().max()) < (3e-6 if K <= 256 else 6e-6) * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,Nsrc,Nq,S,K,N,epi", [(2, 300, 100, 16, 64, 64, 0), (3, 2048, 4000, 16, 64, 64, 1), (2, 512, 5000, 8, 32, 64, 0),
+                                                  (2, 500, 333, 16, 128, 128, 1), (4, 2048, 8192, 16, 64, 64, 1)])
+def test_dense_tc_gather4_tma_is_bit_identical(B, Nsrc, Nq, S, K, N, epi):
+    """Grouped first layer: the neighbour rows fetched by tensor-map TMA (cp.async.bulk.tensor tile::gather4, four rows per
+    instruction, swizzled tiles) against the per-lane cp.async gather: bit-identical outputs (STORE and MAX epilogues, a source
+    array wider than K with a column offset, ragged last tile)."""
+    from ssf_slam_b200 import functional as F_, tc
+    g = torch.Generator().manual_seed(B * 977 + Nq)
+    r = lambda *s: torch.randn(*s, generator=g)
+    G, H, b1, Wd1 = r(B, Nsrc, K + 32).cuda(), r(B, Nq, K).cuda(), r(K).cuda(), (r(3, K) * 0.3).cuda()
+    ps, pq = r(B, Nsrc, 3).cuda(), r(B, Nq, 3).cuda()
+    idx = torch.randint(0, Nsrc, (B, Nq, S), generator=g, dtype=torch.int32).cuda()
+    img = tc.dense_image(r(N, K) / K ** 0.5).cuda()
+    bias = r(N).cuda()
+    outs = {}
+    prev = F_.set_dense_tma(1)
+    try:
+        for on in (True, False):
+            F_.set_dense_tma(2 if on else 0)
+            outs[on] = F_.dense_tc(img, N, K, G=G, offG=32, H=H, b1=b1, Wd1=Wd1, act1=2, idx=idx, pos_src=ps, pos_q=pq, bias=bias, act=1,
+                                   epi=epi).cpu()
+    finally:
+        F_.set_dense_tma(prev)
+    assert torch.equal(outs[True], outs[False])

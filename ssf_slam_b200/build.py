@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libssf_b200.so")
 DEV_LIB = os.path.join(HERE, "libssf_b200_dev.so")   # developer entry points (csrc/dev/), not part of the product ABI
 OBJ_DIR = os.path.join(HERE, "build")
-NVCC_FLAGS = (["-DSSF_CV_TRACE"] if os.environ.get("SSF_CV_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = (["-DSSF_CV_TRACE"] if os.environ.get("SSF_CV_TRACE") else []) + ([] if os.environ.get("SSF_SPLIT_RNA") else ["-DSSF_SPLIT_TRUNC"]) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", os.path.join(os.path.dirname(HERE), "include")]
 
 

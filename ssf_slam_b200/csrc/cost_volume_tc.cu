@@ -61,8 +61,15 @@ __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.syn
 __device__ __forceinline__ void split8(const float* v, float (&hi)[8], float (&lo)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+#ifdef SSF_SPLIT_TRUNC
+        // the tensor core reads an fp32 container as TF32 by dropping the 13 low mantissa bits, so the value itself serves as
+        // its truncated `hi` and only lo = v - trunc(v) (exact) has to be computed: 2 instead of 3 operations per element
+        hi[j] = v[j];
+        lo[j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+#else
         hi[j] = __uint_as_float((__float_as_uint(v[j]) + 0x1000u) & 0xFFFFE000u);
         lo[j] = v[j] - hi[j];
+#endif
     }
 }
 // 32 consecutive columns of this thread's row -> (hi, lo) TMEM images

@@ -478,7 +478,12 @@ def main():
 
     # Independent batches are pipelined over NS CUDA streams (frame pairs carry no cross-batch state): one batch's
     # latency-bound kernels (FPS: 128 CTAs x 1.7 ms) and persistent-kernel tails run under the other batch's dense kernels.
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+    prio = os.environ.get("SSF_STREAM_PRIO")   # experiment: distinct stream priorities (e.g. "-2,-1,0")
+    if prio:
+        pl = [int(v) for v in prio.split(",")]
+        streams = [torch.cuda.Stream(device=dev, priority=pl[i % len(pl)]) for i in range(NS)]
+    else:
+        streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     gatherer = ResultGatherer(dev) if world > 1 else None
 
     def mask_pose(item, flow, masker):

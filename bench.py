@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="index into BASELINE.json configs: 1 (default; 3 is "
                     "the same workload sharded over --gpus ranks), 2 = Seg pipeline N=16384, 4 = N=65536 point-op stress sweep")
-    ap.add_argument("--batch", type=int, default=None, help="frame pairs per step per GPU (default 64; 16 for --config 2)")
+    ap.add_argument("--batch", type=int, default=None, help="frame pairs per step per GPU (default 128; 16 for --config 2)")
     ap.add_argument("--npoints", type=int, default=None)
     ap.add_argument("--pool", type=int, default=200, help="distinct synthetic frame pairs per rank (one sequence)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--ref-pairs-per-step", type=int, default=2, help="--impl reference: frame pairs per step (bounded sample)")
     ap.add_argument("--graph", action="store_true", help="e2e / latency legs: CUDA-graph replay of the step instead of eager "
                     "launches (measured equal on B200: the step is bound by kernel time, not by launch cost)")
-    ap.add_argument("--streams", type=int, default=3, help="CUDA streams independent batches are pipelined over")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams independent batches are pipelined over (measured on B200: "
+                    "2 streams x 128 pairs 2235 frame-pairs/s, 3 x 64 2182, 2 x 192 2240, 2 x 256 2223)")
     ap.add_argument("--masker", default="residual", choices=["residual", "gmm"], help="dynamic-point masker of the step IN BOTH "
                     "ARMS: the residual-vs-rigid-flow masker (north star, DESIGN.md section 5) or the reference's noSeg GMM masker")
     ap.add_argument("--shares-out", default=None, help="write the full per-kernel CUDA-event table (JSON) to this path")
@@ -59,7 +60,7 @@ def parse():
     if a.npoints is None:
         a.npoints = {1: 8192, 2: 16384, 4: 65536}[a.config]
     if a.batch is None:
-        a.batch = {1: 64, 2: 16, 4: 4}[a.config]
+        a.batch = {1: 128, 2: 16, 4: 4}[a.config]
     if a.config == 2:
         a.pool = min(a.pool, 64)
     return a
@@ -270,8 +271,8 @@ def point_op_rooflines(B, N, dev):
     out = []
 
     def traffic(name):
-        t = tr.get(name)
-        return (t["dram_read_bytes"] + t["dram_write_bytes"]) if t is not None and t.get("batch") == B else None
+        t = tr.get(name)   # captured at t["batch"] clouds; these operators' traffic is linear in the number of clouds
+        return (t["dram_read_bytes"] + t["dram_write_bytes"]) * B / t["batch"] if t is not None and t.get("batch") else None
 
     def hbm(name, byts, dram, fn):
         """byts = algorithmic bytes (gathered reads counted as memory reads); dram = compulsory DRAM bytes
@@ -683,9 +684,9 @@ def main():
             roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
                     "traffic": None, "peak_source": pk["source"]}
         tr = traffic_table().get(top)   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same batch only)
-        if tr is not None and tr.get("batch") == B:
-            roof["traffic"] = tr["dram_read_bytes"] + tr["dram_write_bytes"]
-            roof["traffic_source"] = tr["capture"]
+        if tr is not None and tr.get("batch"):
+            roof["traffic"] = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) * B / tr["batch"]
+            roof["traffic_source"] = tr["capture"] + ("" if tr["batch"] == B else "; captured at %d clouds per launch, scaled to %d (the kernel's traffic is linear in the number of clouds)" % (tr["batch"], B))
 
     value = world * B * K / (ms * 1e-3)
     e2e = world * B * K / (ems * 1e-3)

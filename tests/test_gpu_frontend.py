@@ -224,3 +224,34 @@ def test_ros_driver_loops_one_odom_per_cloud_in_order():
     ros = ros_node.Rosless()
     odoms_s = ros_node.run_scene_flow_odometry(ros, SceneFlowFrontEnd(net, n_slots=2, movable=synth.MOVABLE_CLASSES), frames, seg=True)
     check_log(ros, odoms_s, intensity=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_one_process():
+    """Kernels, their stream and the per-device function attributes follow the TENSORS' device, not the current one: a whole
+    forward + mask + pose on cuda:1 while cuda:0 is current gives the same bits as on cuda:0 (large-shared-memory kernels
+    included: FPS at N = 8192, block kNN build, tcgen05 dense layers and cost volume)."""
+    from ssf_slam_b200 import pointnet2_utils as pu, synth
+    from ssf_slam_b200.frontend import SceneFlowFrontEnd, odometry
+    from ssf_slam_b200.model import TFlow
+    from ssf_slam_b200.weights import random_init_state_dict
+    torch.cuda.set_device(0)
+    it = synth.make_pair(5, 8192)
+    net = TFlow()
+    net.load_state_dict(random_init_state_dict(0))
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        fe = SceneFlowFrontEnd(net, device=dev)
+        o = fe.process(it["pos1"][None], it["pos2"][None], return_flow=True)
+        outs.append({k: v.clone() for k, v in o.items()})
+        assert torch.cuda.current_device() == 0
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    x = torch.from_numpy(it["pos1"][None]).to("cuda:1")
+    i0 = pu.furthest_point_sample(x, 2048)
+    assert i0.device == x.device and torch.equal(i0.cpu(), pu.furthest_point_sample(x.to("cuda:0"), 2048).cpu())
+    a = odometry(it["pos1"], it["gt"], device="cuda:1")
+    b = odometry(it["pos1"], it["gt"], device="cuda:0")
+    assert np.array_equal(a["odom"], b["odom"]) and np.array_equal(a["mask"], b["mask"])
+    with pytest.raises(Exception):
+        pu.knn(3, x, x.to("cuda:0"))      # tensors of one call on different devices

@@ -297,3 +297,20 @@ def test_error_behaviour_python_exceptions(pu):
     d, i = pu.knn(1, z(1, 1, 3), z(1, 1, 3))
     assert i.tolist() == [[[0]]] and float(d.abs().max()) == 0.0
     assert pu.ball_query(1.0, 3, z(1, 1, 3), z(1, 1, 3)).tolist() == [[[0, 0, 0]]]
+
+
+def test_query_and_group_modules(pu):
+    """`QueryAndGroup` / `GroupAll` (constructed by the reference at ASF/utils/soflow.py:1520-1523): ball query + grouping with
+    centre-relative coordinates, against the same composition of the oracle's operators."""
+    rng = np.random.default_rng(8)
+    xyz = rng.uniform(-10, 10, (2, 3000, 3)).astype(np.float32)
+    new = xyz[:, ::7][:, :400].copy()
+    feat = rng.standard_normal((2, 6, 3000)).astype(np.float32)
+    got = pu.QueryAndGroup(1.5, 16)(_cuda(xyz), _cuda(new), _cuda(feat)).cpu().numpy()
+    oi, _ = po.c_ball_query(1.5, 16, xyz, new)
+    g_xyz = po.c_group(np.ascontiguousarray(xyz.transpose(0, 2, 1)), oi) - new.transpose(0, 2, 1)[..., None]
+    want = np.concatenate([g_xyz, po.c_group(feat, oi)], axis=1)
+    assert got.shape == (2, 9, 400, 16) and np.array_equal(got, want)
+    assert np.array_equal(pu.QueryAndGroup(1.5, 16, use_xyz=False)(_cuda(xyz), _cuda(new), _cuda(feat)).cpu().numpy(), want[:, 3:])
+    ga = pu.GroupAll()(_cuda(xyz), _cuda(new), _cuda(feat)).cpu().numpy()
+    assert ga.shape == (2, 9, 1, 3000) and np.array_equal(ga[:, :3, 0], xyz.transpose(0, 2, 1)) and np.array_equal(ga[:, 3:, 0], feat)

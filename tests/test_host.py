@@ -207,3 +207,42 @@ def test_carla_subsampler_on_device_matches_reference_golden(golden_dir):
     check_carla_subsampler(dataset.CudaOps(), os.path.join(golden_dir, "carla_subsample.npz"))
     with pytest.raises(ValueError):
         dataset.DeviceFrame([np.zeros((4, 3), np.float32)] * 2, [np.zeros((4, 3), np.float32)] * 2, [np.full(4, 0.5), np.zeros(4)])
+
+
+def test_compat_packages_resolve_to_the_b200_modules():
+    """`from lib import pointnet2_utils` / `import torch_scatter` with ssf_slam_b200/compat on sys.path (what an unmodified
+    reference file does, ASF/utils/utils.py:7, ASF/utils/soflow.py:7,13) bind to our drop-ins; checked in a fresh interpreter."""
+    import subprocess
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "from lib import pointnet2_utils as pu\n"
+            "from torch_scatter import scatter_softmax, scatter_sum\n"
+            "names = ['furthest_point_sample', 'gather_operation', 'knn', 'three_nn', 'grouping_operation', 'ball_query', 'three_interpolate', 'QueryAndGroup', 'GroupAll']\n"
+            "assert all(getattr(pu, n).__module__ == 'ssf_slam_b200.pointnet2_utils' for n in names)\n"
+            "assert scatter_softmax.__module__ == 'ssf_slam_b200.scatter' and scatter_sum.__module__ == 'ssf_slam_b200.scatter'\n"
+            "print('ok')\n") % (os.path.join(ROOT, "ssf_slam_b200", "compat"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/scripts/ActiveSceneFlow/TFlowV3_Occlussion.py"), reason="reference tree not mounted")
+def test_unmodified_reference_model_imports_over_compat():
+    """Build container only: the UNMODIFIED reference model file imports over ssf_slam_b200/compat (its two absent native
+    dependencies resolve to our drop-ins), constructs with the reference's parameter count and, without a GPU, fails loudly in
+    our operator (no CPU fallback) instead of computing anything."""
+    import subprocess
+    code = ("import sys; sys.dont_write_bytecode = True\n"
+            "sys.path[:0] = ['/root/reference/scripts/ActiveSceneFlow', %r, %r]\n"
+            "import torch\n"
+            "from TFlowV3_Occlussion import TFlow\n"
+            "net = TFlow().eval()\n"
+            "assert sum(p.numel() for p in net.parameters()) == 2259344\n"
+            "from ssf_slam_b200._native import SsfError\n"
+            "if not torch.cuda.is_available():\n"
+            "    try:\n"
+            "        net(torch.zeros(1, 3, 2048), torch.zeros(1, 3, 2048))\n"
+            "        raise SystemExit('computed on the CPU')\n"
+            "    except SsfError:\n"
+            "        pass\n"
+            "print('ok')\n") % (os.path.join(ROOT, "ssf_slam_b200", "compat"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-500:], r.stderr[-2000:])

@@ -314,3 +314,29 @@ def test_query_and_group_modules(pu):
     assert np.array_equal(pu.QueryAndGroup(1.5, 16, use_xyz=False)(_cuda(xyz), _cuda(new), _cuda(feat)).cpu().numpy(), want[:, 3:])
     ga = pu.GroupAll()(_cuda(xyz), _cuda(new), _cuda(feat)).cpu().numpy()
     assert ga.shape == (2, 9, 1, 3000) and np.array_equal(ga[:, :3, 0], xyz.transpose(0, 2, 1)) and np.array_equal(ga[:, 3:, 0], feat)
+
+
+def test_index_paths_random_sizes(pu):
+    """Seeded sweep over ragged sizes around every dispatch threshold (scan / one-level / two-level index, warp scan, block
+    counts that are not multiples of 32, super-block counts that are not multiples of 32): kNN and ball query against the C
+    oracle, with duplicates in every cloud."""
+    rng = np.random.default_rng(4242)
+    sizes = [511, 512, 513, 1000, 2047, 2049, 4097, 16384, 16385, 16417, 20011, 32769, 33333, 65537, 100003]
+    for Nr in sizes:
+        B = 1 if Nr > 20000 else 2
+        Nq = int(rng.integers(33, 700))
+        k = int(rng.choice([1, 3, 7, 16, 32]))
+        ref = (rng.standard_normal((B, Nr, 3)) * np.array([30.0, 20.0, 2.0])).astype(np.float32)
+        ref[:, Nr // 3:Nr // 3 + 40] = ref[:, :40]
+        q = np.concatenate([ref[:, :Nq // 2], (rng.standard_normal((B, Nq - Nq // 2, 3)) * 25).astype(np.float32)], axis=1)
+        index = pu.build_index(_cuda(ref))
+        d, i = pu.knn(k, _cuda(q), _cuda(ref), index=index)
+        od, oi = po.c_knn(k, q, ref)
+        assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od), ("knn", Nr, Nq, k)
+        d2, i2 = pu.knn(k, _cuda(q), _cuda(ref))          # the default dispatch for this shape
+        assert np.array_equal(i2.cpu().numpy(), oi), ("knn default", Nr, Nq, k)
+        r = float(rng.choice([0.3, 1.0, 3.0]))
+        ns = int(rng.choice([1, 8, 16, 32]))
+        bi, bc = pu.ball_query(r, ns, _cuda(ref), _cuda(q), return_count=True, index=index)
+        wi, wc = po.c_ball_query(r, ns, ref, q)
+        assert np.array_equal(bc.cpu().numpy(), wc) and np.array_equal(bi.cpu().numpy(), wi), ("ball", Nr, Nq, r, ns)

@@ -14,6 +14,7 @@
 //  * grouping / gather / three_interpolate : vectorised gathers with streaming stores.
 //  * scatter softmax / sum : deterministic (atomic-free accumulation) through a CSR of the key lists.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "ssf_common.cuh"
 
@@ -81,6 +82,252 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ o
         unsigned gm = __reduce_max_sync(0xffffffffu, v2);
         last = (int)__reduce_min_sync(0xffffffffu, v2 == gm ? i2 : 0xffffffffu);
     }
+}
+
+// Pruned variant (2048 < N <= 8192), same result bit for bit.  The distance update of an iteration can only lower the running
+// minimum of points that are closer to the new sample than their current minimum, and after the first few dozen samples that is
+// a small neighbourhood.  So the cloud is first sorted along a Morton curve (bitonic sort in shared memory, as the kNN index
+// build) and kept in shared memory as sorted x / y / z / running-minimum arrays.  32 consecutive sorted points -- a compact
+// blob -- form a "row"; there is one thread per row: sorted row r belongs to warp r % NW (neighbouring rows, which are touched
+// together, go to different warps) as its row j = r / NW, and lane j of that warp keeps the row's bounding box, its largest
+// running minimum and the lowest original index attaining it.  Per iteration lane j bounds the distance from the new sample to
+// box j with the distance's own rounded operations (monotone, so bound <= the computed distance of every point inside); a row
+// is touched only if the bound is below its largest running minimum -- otherwise no minimum in it can change -- and only
+// touched rows (about ten of 256 at N = 8192) update their points and recompute their maximum, up to four rows of a warp at a
+// time so that their shared-memory and warp-reduction latencies overlap.  The iteration is a latency chain, not a throughput
+// problem: few warps (one per 32 rows) keep the issue slots free for it.  The arg-max over rows, warps and the CTA is the same
+// (value, lowest original index) reduction as in fps_kernel; the index travels as index << 13 | sorted slot so that the winner's
+// coordinates are one shared-memory read away.
+template <int U, int NW>
+__device__ __forceinline__ void fps_rows(unsigned& touch, int warp, int lane, int N, const float* sx, const float* sy,
+                                         const float* sz, float* smd, const int* sval, float lx, float ly, float lz,
+                                         float& submax, unsigned& subidx) {
+    int j[U], pos[U];
+    unsigned id[U], rm[U], ri[U];
+    float m[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        j[u] = touch ? __ffs(touch) - 1 : j[0];     // fewer than U rows left: row j[0] again (idempotent)
+        touch &= touch - 1;
+        pos[u] = (j[u] * NW + warp) * 32 + lane;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        id[u] = (unsigned)sval[pos[u]];
+        const float d = ssf_sqdist(sx[pos[u]], sy[pos[u]], sz[pos[u]], lx, ly, lz);
+        m[u] = fminf(smd[pos[u]], d);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) smd[pos[u]] = m[u];
+    // non-negative floats order like their bit patterns; ties resolve to the lowest original index
+#pragma unroll
+    for (int u = 0; u < U; ++u) rm[u] = __reduce_max_sync(0xffffffffu, id[u] < (unsigned)N ? __float_as_uint(m[u]) : 0u);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        ri[u] = __reduce_min_sync(0xffffffffu, (id[u] < (unsigned)N && __float_as_uint(m[u]) == rm[u]) ? (id[u] << 13 | (unsigned)pos[u]) : 0xffffffffu);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (lane == j[u]) {
+            submax = __uint_as_float(rm[u]);
+            subidx = ri[u];
+        }
+}
+
+// T threads (one per row) run the sampling loop; the set-up (keys, sort, scatter) runs on TS = 4 T threads which then leave.
+template <int T>
+__global__ void __launch_bounds__(4 * T, 1)
+fps_pruned_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ out) {
+    constexpr int NW = T / 32, NP = T * 32, TS = 4 * T, NWS = TS / 32;
+    static_assert(NP <= 8192, "index << 13 | slot packing");
+    extern __shared__ float s_dyn[];
+    float* sx = s_dyn;                                   // [NP] sorted coordinates
+    float* sy = sx + NP;
+    float* sz = sy + NP;
+    float* smd = sz + NP;                                // [NP] running minima (the Morton keys during the sort)
+    int* sval = reinterpret_cast<int*>(smd + NP);        // [NP] original index of sorted slot (>= N: padding)
+    unsigned* skey = reinterpret_cast<unsigned*>(smd);
+    __shared__ unsigned long long s_cand[2][NW];        // per warp: value bits << 32 | index << 13 | slot
+    __shared__ float sred[6][NWS];
+    __shared__ float sbb[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* p = xyz + (size_t)blockIdx.x * N * 3;
+    int* o = out + (size_t)blockIdx.x * npoint;
+    // cloud bounding box -> 10-bit Morton keys
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < N; i += TS)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = p[3 * i + c];
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], of));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], of));
+        }
+        if (lane == 0) {
+            sred[c][warp] = mn[c];
+            sred[3 + c][warp] = mx[c];
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float v = sred[tid][0];
+        for (int w = 1; w < NWS; ++w) v = tid < 3 ? fminf(v, sred[tid][w]) : fmaxf(v, sred[tid][w]);
+        sbb[tid] = v;
+    }
+    __syncthreads();
+    {
+        // one scale for the three axes: cells are cubes, so rows are compact in the metric the bound uses
+        const float ext = fmaxf(sbb[3] - sbb[0], fmaxf(sbb[4] - sbb[1], sbb[5] - sbb[2]));
+        const float sc1 = ext > 0.f ? 1023.0f / ext : 0.f;
+        const float sc[3] = {sc1, sc1, sc1};
+        for (int i = tid; i < NP; i += TS) {
+            unsigned key = 0xFFFFFFFFu;
+            if (i < N) {
+                unsigned k3 = 0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float t = (p[3 * i + c] - sbb[c]) * sc[c];
+                    unsigned v = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
+                    v = (v | (v << 16)) & 0x030000FFu;
+                    v = (v | (v << 8)) & 0x0300F00Fu;
+                    v = (v | (v << 4)) & 0x030C30C3u;
+                    v = (v | (v << 2)) & 0x09249249u;
+                    k3 |= v << c;
+                }
+                key = k3;
+            }
+            skey[i] = key;
+            sval[i] = i;
+        }
+    }
+    __syncthreads();
+    for (int size = 2; size <= NP; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (NP >> 1); t += TS) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned ka = skey[lo], kb = skey[hi];
+                const int va = sval[lo], vb = sval[hi];
+                const bool a_gt_b = ka > kb || (ka == kb && va > vb);
+                if (a_gt_b == up) {
+                    skey[lo] = kb; skey[hi] = ka;
+                    sval[lo] = vb; sval[hi] = va;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __shared__ int s_first;                              // sorted slot of original point 0, the first sample
+    for (int i = tid; i < NP; i += TS) {
+        const int id = sval[i];
+        const bool ok = id < N;
+        sx[i] = ok ? p[3 * id] : 0.f;
+        sy[i] = ok ? p[3 * id + 1] : 0.f;
+        sz[i] = ok ? p[3 * id + 2] : 0.f;
+        smd[i] = 1e10f;       // overwrites the keys
+        if (id == 0) s_first = i;
+    }
+    __syncthreads();
+    if (tid >= T) return;
+    auto loop_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory"); };
+    // lane j: box of row j of this warp, its largest running minimum and the lowest index attaining it
+    float blx = INFINITY, bly = INFINITY, blz = INFINITY, bhx = -INFINITY, bhy = -INFINITY, bhz = -INFINITY;
+    float submax = 0.f;
+    unsigned subidx = 0xffffffffu;
+    for (int j = 0; j < 32; ++j) {
+        const int pos = (j * NW + warp) * 32 + lane;
+        const bool ok = sval[pos] < N;
+        float l0 = ok ? sx[pos] : INFINITY, l1 = ok ? sy[pos] : INFINITY, l2 = ok ? sz[pos] : INFINITY;
+        float h0 = ok ? sx[pos] : -INFINITY, h1 = ok ? sy[pos] : -INFINITY, h2 = ok ? sz[pos] : -INFINITY;
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) {
+            l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, of));
+            l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, of));
+            l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, of));
+            h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, of));
+            h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, of));
+            h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, of));
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, ok);
+        if (lane == j) {
+            blx = l0; bly = l1; blz = l2; bhx = h0; bhy = h1; bhz = h2;
+            submax = any ? 1e10f : 0.f;      // an empty row never wins and is never touched
+        }
+    }
+    unsigned last = (unsigned)s_first;       // original index << 13 | sorted slot
+    unsigned wm = 0u, wi = 0xffffffffu;      // this warp's candidate; changes only when one of its rows is touched
+#ifdef SSF_CV_TRACE
+    long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, nrows = 0;
+#define FPS_TR(x) { long long c_ = clock64(); x += c_ - tr0; tr0 = c_; }
+#else
+#define FPS_TR(x)
+#endif
+    for (int it = 0; it < npoint; ++it) {
+        if (tid == 0) o[it] = (int)(last >> 13);
+        if (it == npoint - 1) break;
+#ifdef SSF_CV_TRACE
+        long long tr0 = clock64();
+#endif
+        const int lp = (int)(last & 8191u);
+        const float lx = sx[lp], ly = sy[lp], lz = sz[lp];
+        // lower bound of the distance from the new sample to every point of row `lane` (same rounded operations as ssf_sqdist)
+        const float gx = fmaxf(0.f, fmaxf(__fsub_rn(blx, lx), __fsub_rn(lx, bhx)));
+        const float gy = fmaxf(0.f, fmaxf(__fsub_rn(bly, ly), __fsub_rn(ly, bhy)));
+        const float gz = fmaxf(0.f, fmaxf(__fsub_rn(blz, lz), __fsub_rn(lz, bhz)));
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        unsigned touch = __ballot_sync(0xffffffffu, lb < submax);
+        FPS_TR(tA)
+        if (touch) {   // warp-uniform
+#ifdef SSF_CV_TRACE
+            nrows += __popc(touch);
+#endif
+            if ((touch & (touch - 1)) == 0) {
+                fps_rows<1, NW>(touch, warp, lane, N, sx, sy, sz, smd, sval, lx, ly, lz, submax, subidx);
+            } else if (__popc(touch) == 2) {
+                fps_rows<2, NW>(touch, warp, lane, N, sx, sy, sz, smd, sval, lx, ly, lz, submax, subidx);
+            } else {
+                do {
+                    fps_rows<4, NW>(touch, warp, lane, N, sx, sy, sz, smd, sval, lx, ly, lz, submax, subidx);
+                } while (touch);
+            }
+            FPS_TR(tB)
+            const unsigned vb = subidx != 0xffffffffu ? __float_as_uint(submax) : 0u;
+            wm = __reduce_max_sync(0xffffffffu, vb);
+            wi = __reduce_min_sync(0xffffffffu, vb == wm ? subidx : 0xffffffffu);
+            FPS_TR(tC)
+        }
+        const int buf = it & 1;
+        if (lane == 0) s_cand[buf][warp] = (unsigned long long)wm << 32 | wi;
+        loop_sync();
+        const unsigned long long c = lane < NW ? s_cand[buf][lane] : 0xffffffffull;
+        FPS_TR(tD)
+        const unsigned gm = __reduce_max_sync(0xffffffffu, (unsigned)(c >> 32));
+        last = __reduce_min_sync(0xffffffffu, (unsigned)(c >> 32) == gm ? (unsigned)c : 0xffffffffu);
+        FPS_TR(tE)
+    }
+#ifdef SSF_CV_TRACE
+    if (blockIdx.x == 0 && lane == 0 && (warp < 4 || warp == NW - 1))
+        printf("fps trace N=%d T=%d warp %d: per-iteration cycles  bound+ballot %.0f  rows %.0f (%.2f rows)  warp-redux %.0f  sts+bar+lds %.0f  block-redux %.0f\n",
+               N, T, warp, (double)tA / npoint, (double)tB / npoint, (double)nrows / npoint, (double)tC / npoint, (double)tD / npoint, (double)tE / npoint);
+#endif
+#undef FPS_TR
+}
+
+template <int T>
+static int launch_fps_pruned(const float* xyz, int B, int N, int npoint, int* out, cudaStream_t st) {
+    const size_t smem = (size_t)T * 32 * 20;
+    cudaError_t e = cudaFuncSetAttribute(fps_pruned_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ssf_set_error(e);
+    fps_pruned_kernel<T><<<B, 4 * T, smem, st>>>(xyz, N, npoint, out);
+    ssf_count_launch();
+    SSF_LAUNCH_CHECK();
+    return SSF_OK;
 }
 
 // Cluster variant: CS CTAs of 1024 threads share one cloud (N <= CS * 1024 * PPT); each CTA keeps its slice
@@ -236,6 +483,15 @@ static int launch_fps_cluster(const float* xyz, int B, int N, int npoint, int* o
 extern "C" int ssf_furthest_point_sample(const float* xyz, int B, int N, int npoint, int* idx, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || N <= 0 || npoint <= 0) return ssf_arg_error("furthest_point_sample: empty input");
+    static int prune = -1;   // SSF_FPS_PRUNE=0: the plain kernels everywhere (measurement / regression switch)
+    if (prune < 0) {
+        const char* e = getenv("SSF_FPS_PRUNE");
+        prune = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (prune && N > 2048 && N <= 8192) {
+        if (N <= 4096) return launch_fps_pruned<128>(xyz, B, N, npoint, idx, st);
+        return launch_fps_pruned<256>(xyz, B, N, npoint, idx, st);
+    }
     if (N <= 128) return launch_fps<128, 1>(xyz, B, N, npoint, idx, st);
     if (N <= 256) return launch_fps<128, 2>(xyz, B, N, npoint, idx, st);
     if (N <= 512) return launch_fps<256, 2>(xyz, B, N, npoint, idx, st);

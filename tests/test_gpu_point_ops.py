@@ -72,6 +72,43 @@ def test_fps(pu, N, npoint):
     assert np.array_equal(got, po.c_fps(x, npoint))
 
 
+@pytest.mark.parametrize("case", ["n2049", "n4097", "all_equal", "planar", "line", "clusters", "select_all", "lidar", "tiny_far"])
+def test_fps_pruned_kernel_edge_cases(pu, case):
+    """The spatially pruned sampler (2048 < N <= 8192: Morton rows + box bound, point_ops.cu fps_pruned_kernel) must stay
+    bit-identical to the plain scan of the oracle where its machinery is stressed: nearly empty padded rows, zero extents,
+    massive ties (lowest original index wins), tight clusters far apart, and sampling every point."""
+    rng = np.random.default_rng(abs(hash(case)) % 1000)
+    npoint = 256
+    if case == "n2049":
+        x = _cloud(11, 2, 2049)
+    elif case == "n4097":
+        x = _cloud(12, 2, 4097)
+    elif case == "all_equal":
+        x = np.full((2, 3000, 3), 1.25, np.float32)
+    elif case == "planar":
+        x = _cloud(13, 2, 6000)
+        x[..., 2] = 0.5
+    elif case == "line":
+        x = np.zeros((2, 5000, 3), np.float32)
+        x[..., 0] = rng.uniform(-50, 50, (2, 5000)).astype(np.float32)
+    elif case == "clusters":
+        c = rng.uniform(-80, 80, (2, 12, 1, 3))
+        x = (c + rng.standard_normal((2, 12, 600, 3)) * 0.05).reshape(2, 7200, 3).astype(np.float32)
+        x = x[:, rng.permutation(7200)]
+    elif case == "select_all":
+        x = _cloud(14, 1, 2500)
+        npoint = 2500
+    elif case == "lidar":
+        from ssf_slam_b200 import synth
+        x = np.stack([it["pos1"] for it in synth.make_sequence(77, 2, 8192)]).astype(np.float32)
+        npoint = 2048
+    else:
+        x = (rng.standard_normal((2, 8192, 3)) * 1e-3).astype(np.float32)
+        x[:, 100] += 1e4      # one far outlier squeezes everything else into one Morton cell
+    got = pu.furthest_point_sample(_cuda(x), npoint).cpu().numpy()
+    assert np.array_equal(got, po.c_fps(np.ascontiguousarray(x), npoint))
+
+
 @pytest.mark.parametrize("Nq,Nr,k", [(2048, 8192, 16), (8192, 8192, 16), (8192, 2048, 7), (512, 256, 5), (128, 256, 8),
                                      (8192, 2048, 3), (1000, 1501, 16), (77, 33, 32), (3, 1, 1), (4096, 5000, 16)])
 def test_knn(pu, Nq, Nr, k):

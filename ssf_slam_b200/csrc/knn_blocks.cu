@@ -18,7 +18,7 @@
 #include <math_constants.h>
 
 #ifdef SSF_CV_TRACE
-__device__ unsigned long long g_knn_stat[4];   // queries, visits, inserts, sweep re-checks
+__device__ unsigned long long g_knn_stat[8];   // queries, visits, inserts (a merge = 8), sweep re-checks, merges, survivors
 #define KSTAT(i, n) do { if (lane == 0) atomicAdd(&g_knn_stat[i], (unsigned long long)(n)); } while (0)
 #else
 #define KSTAT(i, n) do {} while (0)
@@ -32,14 +32,6 @@ constexpr int KB_BUILD_T = 1024;
 // of one batch run in the issue slots the tensor kernels of another batch leave idle (they issue ~40 % of the time).
 constexpr int KB_SEARCH_T = 128;                       // threads per search CTA
 constexpr int KB_QPB = (KB_SEARCH_T / 32) * 8;         // queries per search CTA (8 per warp)
-
-__device__ __forceinline__ unsigned morton_spread(unsigned v) {   // 10 bits -> every third bit
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
 
 // ws layout per cloud (floats): pts4 [npad][4] | box_lo [nblk][4] | box_hi [nblk][4]
 __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const float* __restrict__ ref, int Nr, int npow2, int npad,
@@ -80,11 +72,12 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
         sbb[tid] = v;
     }
     __syncthreads();
+    // one scale for the three axes: Morton cells are cubes, so the 32-point blocks are compact in the metric the search prunes
+    // with (per-axis scales make 4 cm x 9 m slivers out of a 200 m x 23 m x 10 m LiDAR sweep and cost ~70 % more block visits)
     float sc[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float ext = sbb[3 + c] - sbb[c];
-        sc[c] = ext > 0.f ? 1023.0f / ext : 0.f;
+    {
+        const float ext = fmaxf(sbb[3] - sbb[0], fmaxf(sbb[4] - sbb[1], sbb[5] - sbb[2]));
+        sc[0] = sc[1] = sc[2] = ext > 0.f ? 1023.0f / ext : 0.f;
     }
     for (int i = tid; i < npow2; i += KB_BUILD_T) {
         unsigned key = 0xFFFFFFFFu;
@@ -95,7 +88,7 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
                 const float t = (rp[3 * i + c] - sbb[c]) * sc[c];
                 q[c] = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
             }
-            key = morton_spread(q[0]) | (morton_spread(q[1]) << 1) | (morton_spread(q[2]) << 2);
+            key = ssf_hilbert30(q[0], q[1], q[2]);
         }
         skey[i] = key;
         sval[i] = i;
@@ -210,7 +203,9 @@ __global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search_kernel(int 
             const float4 p = __ldg(P + (size_t)blk * 32 + lane);
             unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
             unsigned mask = __ballot_sync(0xffffffffu, key < kth);
+            KSTAT(5, __popc(mask));
             if (__popc(mask) >= merge_min) {
+                KSTAT(4, 1);
                 // many survivors (the first blocks of a query): sort the block and merge it with the list in one go -- the
                 // element-wise min of the list and the reversed block is a bitonic sequence holding the 32 smallest keys
                 key = sort32(key);
@@ -444,11 +439,12 @@ __global__ void __launch_bounds__(KB_RADIX_T) knn_blocks_build_large_kernel(cons
         sbb[tid] = v;
     }
     __syncthreads();
+    // one scale for the three axes: Morton cells are cubes, so the 32-point blocks are compact in the metric the search prunes
+    // with (per-axis scales make 4 cm x 9 m slivers out of a 200 m x 23 m x 10 m LiDAR sweep and cost ~70 % more block visits)
     float sc[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float ext = sbb[3 + c] - sbb[c];
-        sc[c] = ext > 0.f ? 1023.0f / ext : 0.f;
+    {
+        const float ext = fmaxf(sbb[3] - sbb[0], fmaxf(sbb[4] - sbb[1], sbb[5] - sbb[2]));
+        sc[0] = sc[1] = sc[2] = ext > 0.f ? 1023.0f / ext : 0.f;
     }
     for (int i = tid; i < npad; i += KB_RADIX_T) {
         unsigned key = 0xFFFFFFFFu;      // padding sorts last (real keys have 30 bits)
@@ -459,7 +455,7 @@ __global__ void __launch_bounds__(KB_RADIX_T) knn_blocks_build_large_kernel(cons
                 const float t = (rp[3 * i + c] - sbb[c]) * sc[c];
                 q[c] = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
             }
-            key = morton_spread(q[0]) | (morton_spread(q[1]) << 1) | (morton_spread(q[2]) << 2);
+            key = ssf_hilbert30(q[0], q[1], q[2]);
         }
         keyA[i] = key;
         valA[i] = i;
@@ -790,8 +786,8 @@ inline int next_pow2(int v) {
 
 #ifdef SSF_CV_TRACE
 extern "C" int ssf_knn_stat_read(unsigned long long* out, int reset) {
-    if (cudaMemcpyFromSymbol(out, g_knn_stat, sizeof(unsigned long long) * 4) != cudaSuccess) return 2;
-    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_knn_stat, z, sizeof(z)); }
+    if (cudaMemcpyFromSymbol(out, g_knn_stat, sizeof(unsigned long long) * 8) != cudaSuccess) return 2;
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_knn_stat, z, sizeof(z)); }
     return 0;
 }
 #endif

@@ -188,18 +188,13 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restr
         for (int i = tid; i < NP; i += TS) {
             unsigned key = 0xFFFFFFFFu;
             if (i < N) {
-                unsigned k3 = 0;
+                unsigned q[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float t = (p[3 * i + c] - sbb[c]) * sc[c];
-                    unsigned v = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
-                    v = (v | (v << 16)) & 0x030000FFu;
-                    v = (v | (v << 8)) & 0x0300F00Fu;
-                    v = (v | (v << 4)) & 0x030C30C3u;
-                    v = (v | (v << 2)) & 0x09249249u;
-                    k3 |= v << c;
+                    q[c] = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
                 }
-                key = k3;
+                key = ssf_hilbert30(q[0], q[1], q[2]);
             }
             skey[i] = key;
             sval[i] = i;

@@ -17,3 +17,11 @@ def t(fn):
     return e0.elapsed_time(e1) / 5
 print(os.environ.get("TAG"), "k16 8192x8192 %.3f  k7 8192x8192 %.3f  k16 8192x2048 %.3f  k16 2048x8192 %.3f  k16 2048x2048 %.3f" % (
     t(lambda: F_.knn_idx(16, x1, x2)), t(lambda: F_.knn_idx(7, x1, x2)), t(lambda: F_.knn_idx(16, x1, sub)), t(lambda: F_.knn_idx(16, sub, x1)), t(lambda: F_.knn_idx(16, sub, sub))))
+
+
+def build(ref):
+    F_.knn_cache_clear()
+    F_._knn_blocks(ref)
+
+
+print(os.environ.get("TAG"), "index build (B=%d): 8192 pts %.3f ms  2048 pts %.3f ms" % (B, t(lambda: build(x2)), t(lambda: build(sub))))

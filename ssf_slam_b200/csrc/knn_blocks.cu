@@ -36,9 +36,7 @@ constexpr int KB_QPB = (KB_SEARCH_T / 32) * 8;         // queries per search CTA
 // ws layout per cloud (floats): pts4 [npad][4] | box_lo [nblk][4] | box_hi [nblk][4]
 __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const float* __restrict__ ref, int Nr, int npow2, int npad,
                                                                        int nblk, float* __restrict__ ws) {
-    extern __shared__ __align__(16) unsigned sm_u[];
-    unsigned* skey = sm_u;              // [npow2]
-    int* sval = reinterpret_cast<int*>(sm_u + npow2);   // [npow2]
+    extern __shared__ __align__(16) unsigned long long skv[];   // [npow2] Hilbert key << 32 | point index
     __shared__ float sred[6][32];
     __shared__ float sbb[6];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,28 +88,11 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
             }
             key = ssf_hilbert30(q[0], q[1], q[2]);
         }
-        skey[i] = key;
-        sval[i] = i;
+        skv[i] = (unsigned long long)key << 32 | (unsigned)i;
     }
     __syncthreads();
-    // bitonic sort on (key, val): val breaks key ties so the layout is a deterministic function of the cloud
-    for (int size = 2; size <= npow2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (npow2 >> 1); t += KB_BUILD_T) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned ka = skey[lo], kb = skey[hi];
-                const int va = sval[lo], vb = sval[hi];
-                const bool a_gt_b = ka > kb || (ka == kb && va > vb);
-                if (a_gt_b == up) {
-                    skey[lo] = kb; skey[hi] = ka;
-                    sval[lo] = vb; sval[hi] = va;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    // sort on (key, index): the index breaks key ties, so the layout is a deterministic function of the cloud
+    ssf_cta_sort_u64(skv, npow2, tid, KB_BUILD_T);
     // sorted points (padding: +inf coordinates, index INT_MAX -> never selected) and per-block boxes
     float4* pts4 = reinterpret_cast<float4*>(wsb);
     float4* blo = pts4 + npad;
@@ -120,7 +101,7 @@ __global__ void __launch_bounds__(KB_BUILD_T) knn_blocks_build_kernel(const floa
         float4 p = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(0x7fffffff));
         float lo3[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi3[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
         if (i < Nr) {
-            const int o = sval[i];
+            const int o = (int)(unsigned)skv[i];
             p = make_float4(rp[3 * o], rp[3 * o + 1], rp[3 * o + 2], __int_as_float(o));
             lo3[0] = hi3[0] = p.x; lo3[1] = hi3[1] = p.y; lo3[2] = hi3[2] = p.z;
         }
@@ -821,7 +802,7 @@ extern "C" int ssf_knn_blocks_build(const float* ref, int B, int Nr, float* ws, 
         SSF_LAUNCH_CHECK();
         return SSF_OK;
     }
-    const int npow2 = next_pow2(Nr), npad = (Nr + 31) / 32 * 32, nblk = npad / 32;
+    const int npow2 = next_pow2(Nr) < 256 ? 256 : next_pow2(Nr), npad = (Nr + 31) / 32 * 32, nblk = npad / 32;   // the CTA sort works on runs of 256
     const size_t smem = (size_t)npow2 * 8;
     static unsigned long long attr_set = 0;
     if (ssf_attr_needed(&attr_set)) {

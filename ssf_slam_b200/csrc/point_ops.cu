@@ -139,13 +139,13 @@ __global__ void __launch_bounds__(4 * T, 1)
 fps_pruned_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ out) {
     constexpr int NW = T / 32, NP = T * 32, TS = 4 * T, NWS = TS / 32;
     static_assert(NP <= 8192, "index << 13 | slot packing");
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(16) float s_dyn[];
     float* sx = s_dyn;                                   // [NP] sorted coordinates
     float* sy = sx + NP;
     float* sz = sy + NP;
     float* smd = sz + NP;                                // [NP] running minima (the Morton keys during the sort)
     int* sval = reinterpret_cast<int*>(smd + NP);        // [NP] original index of sorted slot (>= N: padding)
-    unsigned* skey = reinterpret_cast<unsigned*>(smd);
+    unsigned long long* skv = reinterpret_cast<unsigned long long*>(smd);   // [NP] key << 32 | index during the sort: smd + sval
     __shared__ unsigned long long s_cand[2][NW];        // per warp: value bits << 32 | index << 13 | slot
     __shared__ float sred[6][NWS];
     __shared__ float sbb[6];
@@ -196,37 +196,31 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restr
                 }
                 key = ssf_hilbert30(q[0], q[1], q[2]);
             }
-            skey[i] = key;
-            sval[i] = i;
+            skv[i] = (unsigned long long)key << 32 | (unsigned)i;
         }
     }
     __syncthreads();
-    for (int size = 2; size <= NP; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (NP >> 1); t += TS) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned ka = skey[lo], kb = skey[hi];
-                const int va = sval[lo], vb = sval[hi];
-                const bool a_gt_b = ka > kb || (ka == kb && va > vb);
-                if (a_gt_b == up) {
-                    skey[lo] = kb; skey[hi] = ka;
-                    sval[lo] = vb; sval[hi] = va;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    ssf_cta_sort_u64(skv, NP, tid, TS);
     __shared__ int s_first;                              // sorted slot of original point 0, the first sample
+    // sorted coordinates; then the (key, index) pairs make room for the running minima and the indices
     for (int i = tid; i < NP; i += TS) {
-        const int id = sval[i];
+        const int id = (int)(unsigned)skv[i];
         const bool ok = id < N;
         sx[i] = ok ? p[3 * id] : 0.f;
         sy[i] = ok ? p[3 * id + 1] : 0.f;
         sz[i] = ok ? p[3 * id + 2] : 0.f;
-        smd[i] = 1e10f;       // overwrites the keys
         if (id == 0) s_first = i;
+    }
+    {
+        int ids[(NP + TS - 1) / TS];
+#pragma unroll
+        for (int u = 0; u < (NP + TS - 1) / TS; ++u) ids[u] = (int)(unsigned)skv[tid + u * TS];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < (NP + TS - 1) / TS; ++u) {
+            smd[tid + u * TS] = 1e10f;
+            sval[tid + u * TS] = ids[u];
+        }
     }
     __syncthreads();
     if (tid >= T) return;

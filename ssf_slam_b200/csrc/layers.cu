@@ -330,11 +330,122 @@ interpolate_kernel(const float* __restrict__ query, const float* __restrict__ sr
     }
 }
 
+// Up to 128 channels in 16-byte pieces: LPQ = 8 / 16 / 32 lanes per query point, so a warp interpolates 4 / 2 / 1 points at once
+// (C = 64: half the warps of the warp-per-point kernel, C = 96: one 16-byte pass instead of three scalar ones).  mode 0,
+// C % 4 == 0, C <= 4 LPQ, k <= LPQ; same operations in the same order as interpolate_kernel.
+template <int LPQ>
+__global__ void __launch_bounds__(128)
+interpolate_group_kernel(const float* __restrict__ query, const float* __restrict__ src_pos, const float* __restrict__ src_val,
+                         const int* __restrict__ idx, int ld_idx, int N, int M, int C, int k, float clampv,
+                         float* __restrict__ out) {
+    constexpr int QPW = 32 / LPQ;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, g = lane / LPQ, l = lane % LPQ;
+    const int n_raw = (blockIdx.x * 4 + (threadIdx.x >> 5)) * QPW + g;
+    const bool live = n_raw < N;
+    const int n = live ? n_raw : N - 1;      // idle groups of the last warp shadow the last point (full-mask shuffles)
+    const float* q = query + ((size_t)b * N + n) * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    float inv = 0.f;
+    int id = 0;
+    if (l < k) {
+        id = idx[((size_t)b * N + n) * ld_idx + l];
+        const float* s = src_pos + ((size_t)b * M + id) * 3;
+        const float dx = s[0] - qx, dy = s[1] - qy, dz = s[2] - qz;
+        const float d = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-10f);
+        inv = 1.0f / d;
+    }
+    float norm = 0.f;
+    for (int j = 0; j < k; ++j) norm += __shfl_sync(0xffffffffu, inv, g * LPQ + j);  // slot order, as torch.sum over the last dim
+    const float w = inv / norm;
+    const int c = l * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < k; ++j) {
+        const float wj = __shfl_sync(0xffffffffu, w, g * LPQ + j);
+        const int ij = __shfl_sync(0xffffffffu, id, g * LPQ + j);
+        if (c < C) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(src_val + ((size_t)b * M + ij) * C + c));
+            v[0] += wj * x.x; v[1] += wj * x.y; v[2] += wj * x.z; v[3] += wj * x.w;
+        }
+    }
+    if (live && c < C) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = fminf(fmaxf(v[u], -clampv), clampv);
+        *reinterpret_cast<float4*>(out + ((size_t)b * N + n) * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// Few channels (C <= 4: the coarse flow of UpsampleFlow and PointWarping): one THREAD per query point -- a warp per point leaves
+// 29 of 32 lanes idle and makes every point its own dependent load chain.  Same operations in the same order as above.
+__global__ void __launch_bounds__(128)
+interpolate_thread_kernel(const float* __restrict__ query, const float* __restrict__ src_pos, const float* __restrict__ src_val,
+                          const int* __restrict__ idx, int ld_idx, int N, int M, int C, int k, int mode, float clampv,
+                          float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const float* q = query + ((size_t)b * N + n) * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    const int* ip = idx + ((size_t)b * N + n) * ld_idx;
+    float inv[16];
+    int id[16];
+    float norm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j < k) {
+            id[j] = ip[j];
+            const float* s = src_pos + ((size_t)b * M + id[j]) * 3;
+            const float dx = s[0] - qx, dy = s[1] - qy, dz = s[2] - qz;
+            const float d = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-10f);
+            inv[j] = 1.0f / d;
+            norm += inv[j];   // slot order, as torch.sum over the last dim
+        }
+    }
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j < k) {
+            const float wj = inv[j] / norm;
+            const float* sp = src_val + ((size_t)b * M + id[j]) * C;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < C) v[c] += wj * __ldg(sp + c);
+        }
+    }
+    float* op = out + ((size_t)b * N + n) * C;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < C) {
+            float r = v[c];
+            if (mode == 1) r = (c == 0 ? qx : (c == 1 ? qy : qz)) - r;
+            op[c] = fminf(fmaxf(r, -clampv), clampv);
+        }
+}
+
 extern "C" int ssf_interpolate(const float* query, const float* src_pos, const float* src_val, const int* idx, int ld_idx, int B,
                                int N, int M, int C, int k, int mode, float clampv, float* out, void* stream) {
     if (B <= 0 || N <= 0 || C <= 0) return ssf_arg_error("interpolate: empty input");
     if (k <= 0 || k > 16 || ld_idx < k) return ssf_arg_error("interpolate: k must be in [1,16] and ld_idx >= k");
     if (mode == 1 && C != 3) return ssf_arg_error("interpolate: warp mode needs C == 3");
+    if (C <= 4) {
+        interpolate_thread_kernel<<<dim3((N + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, mode, clampv, out);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
+    const bool al16g = ((reinterpret_cast<uintptr_t>(src_val) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (mode == 0 && C % 4 == 0 && C <= 128 && k <= 8 && al16g) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (C <= 32)
+            interpolate_group_kernel<8><<<dim3((N + 15) / 16, B), 128, 0, st>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, clampv, out);
+        else if (C <= 64)
+            interpolate_group_kernel<16><<<dim3((N + 7) / 8, B), 128, 0, st>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, clampv, out);
+        else
+            interpolate_group_kernel<32><<<dim3((N + 3) / 4, B), 128, 0, st>>>(query, src_pos, src_val, idx, ld_idx, N, M, C, k, clampv, out);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
     dim3 grid((N + 3) / 4, B);
     const bool al16 = ((reinterpret_cast<uintptr_t>(src_val) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if (mode == 0 && C % 128 == 0 && al16)

@@ -454,3 +454,29 @@ def test_upsample_flow_channel_widths(C, k):
     want = tp.upsample_flow(xyz.transpose(1, 2).contiguous(), sparse.transpose(1, 2).contiguous(), val.transpose(1, 2).contiguous(), k)
     assert got.shape == (2, 700, C)
     assert float((got - want.transpose(1, 2)).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("C,k,mode", [(3, 5, 0), (3, 7, 0), (4, 3, 0), (1, 16, 0), (3, 7, 1), (3, 3, 1), (64, 5, 0), (64, 3, 0),
+                                      (96, 3, 0), (128, 7, 0), (32, 3, 0), (8, 8, 0), (64, 16, 0)])
+def test_interpolate_kernel_variants_are_bit_identical(C, k, mode):
+    """C <= 4 runs one thread per query (layers.cu interpolate_thread_kernel), C <= 128 in 16-byte pieces 8 / 16 / 32 lanes per
+    query (interpolate_group_kernel, k <= 8), everything else one warp per query.  Same operations in the same order: the first
+    C channels of a zero-padded 256-channel call (warp kernel) must be bit-identical; mode 1 (PointWarping, C == 3 only) is
+    checked against query - v of the mode-0 result, clamped."""
+    from ssf_slam_b200 import functional as F_
+    g = torch.Generator().manual_seed(10 * C + k)
+    q = (torch.randn(2, 1111, 3, generator=g) * 10).cuda()
+    sp = (torch.randn(2, 300, 3, generator=g) * 10).cuda()
+    sp[:, :5] = q[:, :5]      # coincident points: the 1e-10 distance floor
+    val = torch.randn(2, 300, C, generator=g).cuda()
+    idx = F_.knn_idx(16, q, sp)
+    wide = torch.zeros(2, 300, 256, device="cuda")
+    wide[..., :C] = val
+    ref = F_.interpolate(q, sp, wide, idx, mode=0, clampv=100.0, k=k)[..., :C]
+    if mode == 0:
+        got = F_.interpolate(q, sp, val, idx, mode=0, clampv=100.0, k=k)
+        assert torch.equal(got, ref)
+    else:
+        got = F_.interpolate(q, sp, val, idx, mode=1, clampv=10.0, k=k)
+        unclamped = F_.interpolate(q, sp, wide, idx, mode=0, clampv=3.0e38, k=k)[..., :3]
+        assert torch.equal(got, (q - unclamped).clamp(-10.0, 10.0))

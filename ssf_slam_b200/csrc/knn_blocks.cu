@@ -16,6 +16,7 @@
 // just in exact arithmetic; blocks are skipped only on bound > kth (strict), so index ties are never lost.
 #include "ssf_common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 #ifdef SSF_CV_TRACE
 __device__ unsigned long long g_knn_stat[8];   // queries, visits, inserts (a merge = 8), sweep re-checks, merges, survivors
@@ -272,6 +273,174 @@ __global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search_kernel(int 
                 KSTAT(3, 1);
                 if (blb > kth_d) continue;   // warp-uniform
                 visit(s * 32 + bl);
+            }
+        }
+        if (lane < k) {
+            const size_t o = ((size_t)b * Nq + qi) * k + lane;
+            idx[o] = (int)(unsigned)(list_k & 0xffffffffull);
+            if (dist != nullptr) dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(list_k >> 32)));
+        }
+    }
+}
+
+// Search for 64 < nblk <= 512 blocks (2048 < Nr <= 16384).  Holding every block bound in registers (8-16 per lane) makes the
+// bound computation and every arg-min over them the largest part of a query once the Hilbert order has cut the visits to 3-4
+// blocks.  So the bounds are taken in two steps: a lane first bounds ONE super-box (the union of SUPB consecutive blocks: a
+// compact run of the curve; the unions are made in the prologue from the block boxes already in shared memory), the warp
+// picks the 32 / SUPB nearest super-boxes and spreads their 32 blocks over the lanes -- one bound, one register, and an
+// arg-min is a reduction plus a ballot.  More super-boxes are opened only while one is at most the k-th distance away
+// (rare).  Every block whose bound does not exceed the final k-th distance is still visited: a block of a super-box that was
+// never opened is at least as far as the super-box, which was beyond the k-th distance when it was last tested, and that
+// distance only shrinks.  Same keys and list operations as above, so the same result.
+template <int SUPB>
+__global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search_sb_kernel(int k, const float* __restrict__ query, const float* __restrict__ qadd,
+                                                                   const float* __restrict__ ws, int Nq, int npad, int nblk,
+                                                                   float* __restrict__ dist, int* __restrict__ idx) {
+    constexpr int EXP = 32 / SUPB;      // super-boxes opened per round
+    constexpr int merge_min = 12;
+    extern __shared__ __align__(16) float4 sbox[];   // [nblk] lo | [nblk] hi | [32] super lo | [32] super hi
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const float* wsb = ws + (size_t)b * ((size_t)npad * 4 + (size_t)nblk * 8);
+    const float4* P = reinterpret_cast<const float4*>(wsb);
+    {
+        const float4* src = P + npad;
+        for (int i = tid; i < 2 * nblk; i += KB_SEARCH_T) sbox[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    float4* ssup = sbox + 2 * nblk;
+    if (tid < 32) {
+        float4 lo = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f), hi = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
+        for (int u = 0; u < SUPB; ++u) {
+            const int blk = tid * SUPB + u;
+            if (blk < nblk) {
+                const float4 l = sbox[blk], h = sbox[nblk + blk];
+                lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
+                hi.x = fmaxf(hi.x, h.x); hi.y = fmaxf(hi.y, h.y); hi.z = fmaxf(hi.z, h.z);
+            }
+        }
+        ssup[tid] = lo;        // an empty super-box keeps (+inf, -inf): its bound is +inf
+        ssup[32 + tid] = hi;
+    }
+    __syncthreads();
+    auto box_bound = [](const float4 lo, const float4 hi, float qx, float qy, float qz) -> float {
+        const float gx = fmaxf(0.f, fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)));
+        const float gy = fmaxf(0.f, fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)));
+        const float gz = fmaxf(0.f, fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)));
+        return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+    };
+    constexpr unsigned INF_BITS = 0x7f800000u;
+    const int q_end = min(Nq, (int)(blockIdx.x + 1) * KB_QPB);
+    for (int qi = blockIdx.x * KB_QPB + warp; qi < q_end; qi += KB_SEARCH_T / 32) {
+        const float* qp = query + ((size_t)b * Nq + qi) * 3;
+        float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        if (qadd != nullptr) {
+            const float* ap = qadd + ((size_t)b * Nq + qi) * 3;
+            qx = __fadd_rn(qx, __ldg(ap));
+            qy = __fadd_rn(qy, __ldg(ap + 1));
+            qz = __fadd_rn(qz, __ldg(ap + 2));
+        }
+        KSTAT(0, 1);
+        unsigned slb = __float_as_uint(box_bound(ssup[lane], ssup[32 + lane], qx, qy, qz));   // bounds are >= 0: bits order like values
+        unsigned long long list_k = 0x7f8000007fffffffull, kth = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+        float kth_d = CUDART_INF_F;
+        auto pack = [](float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; };
+        auto sort32 = [&](unsigned long long key) -> unsigned long long {
+#pragma unroll
+            for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool take_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                    if (take_min == (ok < key)) key = ok;
+                }
+            }
+            return key;
+        };
+        auto visit = [&](int blk) {
+            KSTAT(1, 1);
+            const float4 p = __ldg(P + (size_t)blk * 32 + lane);
+            unsigned long long key = pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+            unsigned mask = __ballot_sync(0xffffffffu, key < kth);
+            KSTAT(5, __popc(mask));
+            if (__popc(mask) >= merge_min) {
+                KSTAT(4, 1);
+                key = sort32(key);
+                const unsigned long long rev = __shfl_sync(0xffffffffu, key, 31 - lane);
+                unsigned long long m = rev < list_k ? rev : list_k;
+#pragma unroll
+                for (int j = 16; j > 0; j >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, m, j);
+                    if (((lane & j) == 0) == (ok < m)) m = ok;
+                }
+                list_k = m;
+                kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+                KSTAT(2, 8);
+            } else {
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned long long ck = __shfl_sync(0xffffffffu, key, src);
+                    if (ck >= kth) continue;   // warp-uniform: the k-th key tightened meanwhile
+                    KSTAT(2, 1);
+                    const int pos = __popc(__ballot_sync(0xffffffffu, list_k < ck));
+                    const unsigned long long uk = __shfl_up_sync(0xffffffffu, list_k, 1);
+                    list_k = lane == pos ? ck : (lane > pos ? uk : list_k);
+                    kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+                }
+            }
+            kth_d = __uint_as_float((unsigned)(kth >> 32));
+        };
+        bool seeded = false;
+#pragma unroll 1
+        for (;;) {
+            // open the (up to) EXP nearest super-boxes that can still hold a better point; lanes [e SUPB, (e + 1) SUPB) take the e-th
+            int mysb = -1, opened = 0;
+#pragma unroll
+            for (int e = 0; e < EXP; ++e) {
+                const unsigned mn = __reduce_min_sync(0xffffffffu, slb);
+                if (mn == INF_BITS || __uint_as_float(mn) > kth_d) break;   // warp-uniform
+                const int L = __ffs(__ballot_sync(0xffffffffu, slb == mn)) - 1;
+                if (lane == L) slb = INF_BITS;
+                if (lane / SUPB == e) mysb = L;
+                ++opened;
+            }
+            if (opened == 0) break;
+            int blk = -1;
+            unsigned lbk = INF_BITS;
+            if (mysb >= 0 && mysb * SUPB + lane % SUPB < nblk) {
+                blk = mysb * SUPB + lane % SUPB;
+                lbk = __float_as_uint(box_bound(sbox[blk], sbox[nblk + blk], qx, qy, qz));
+            }
+            // nearest-first: the seed block (its 32 points, sorted across the lanes, become the list) and a few visits that
+            // tighten the k-th distance quickly
+            const int nrep = seeded ? 1 : 4;
+#pragma unroll 1
+            for (int rep = 0; rep < nrep; ++rep) {
+                const unsigned mn = __reduce_min_sync(0xffffffffu, lbk);
+                if (mn == INF_BITS || __uint_as_float(mn) > kth_d) break;
+                const int L = __ffs(__ballot_sync(0xffffffffu, lbk == mn)) - 1;
+                const int vb = __shfl_sync(0xffffffffu, blk, L);
+                if (lane == L) lbk = INF_BITS;
+                if (!seeded) {
+                    const float4 p = __ldg(P + (size_t)vb * 32 + lane);
+                    list_k = sort32(pack(ssf_sqdist(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)));
+                    kth = __shfl_sync(0xffffffffu, list_k, k - 1);
+                    kth_d = __uint_as_float((unsigned)(kth >> 32));
+                    seeded = true;
+                } else {
+                    visit(vb);
+                }
+            }
+            // the rest of the opened blocks in lane order under the (shrinking) k-th distance
+            unsigned m = __ballot_sync(0xffffffffu, lbk != INF_BITS && __uint_as_float(lbk) <= kth_d);
+            while (m) {
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const float blb = __uint_as_float(__shfl_sync(0xffffffffu, lbk, L));
+                KSTAT(3, 1);
+                if (blb > kth_d) continue;   // warp-uniform
+                visit(__shfl_sync(0xffffffffu, blk, L));
             }
         }
         if (lane < k) {
@@ -837,6 +1006,23 @@ extern "C" int ssf_knn_blocks_search(int k, const float* query, const float* que
         return SSF_OK;
     }
     const size_t smem = (size_t)nblk * 32;
+    static int use_sb = -1;   // SSF_KNN_SB=0: the register-resident bounds for every size (measurement switch)
+    if (use_sb < 0) {
+        const char* e = getenv("SSF_KNN_SB");
+        use_sb = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (use_sb && nblk > 64) {
+        const size_t smem_sb = smem + 64 * 16;
+        if (nblk <= 128)
+            knn_blocks_search_sb_kernel<4><<<grid, KB_SEARCH_T, smem_sb, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+        else if (nblk <= 256)
+            knn_blocks_search_sb_kernel<8><<<grid, KB_SEARCH_T, smem_sb, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+        else
+            knn_blocks_search_sb_kernel<16><<<grid, KB_SEARCH_T, smem_sb, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
     if (nblk <= 64)
         knn_blocks_search_kernel<2><<<grid, KB_SEARCH_T, smem, st>>>(k, query, query_add, ws, Nq, npad, nblk, dist, idx);
     else if (nblk <= 256)

@@ -13,6 +13,7 @@ and ``torch_scatter`` re-exporting this module and ``ssf_slam_b200.scatter``.
 import torch
 
 from . import _native as nat
+from . import functional as F_
 
 
 def _f32(t):
@@ -81,7 +82,7 @@ def knn(k, unknown, known, offset=None, index=None):
     idx = torch.empty(B, Nq, k, dtype=torch.int32, device=unknown.device)
     off = None if offset is None else _f32(offset)
     L = nat.lib()
-    if index is not None or 512 <= Nr <= 16384 or (16384 < Nr <= INDEX_MAX_POINTS and B * Nq > 32768):
+    if index is not None or F_.KNN_BLOCKS_MIN_REF <= Nr <= 16384 or (16384 < Nr <= INDEX_MAX_POINTS and B * Nq > 32768):
         # Morton-block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster; above 16384
         # reference points a two-level index (radix-sorted build, super-blocks of 32 blocks)
         ws = index if index is not None else build_index(known)

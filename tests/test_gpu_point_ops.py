@@ -358,7 +358,7 @@ def test_index_paths_random_sizes(pu):
     counts that are not multiples of 32, super-block counts that are not multiples of 32): kNN and ball query against the C
     oracle, with duplicates in every cloud."""
     rng = np.random.default_rng(4242)
-    sizes = [511, 512, 513, 1000, 2047, 2049, 4097, 16384, 16385, 16417, 20011, 32769, 33333, 65537, 100003]
+    sizes = [65, 255, 256, 257, 511, 512, 513, 1000, 2047, 2049, 4097, 16384, 16385, 16417, 20011, 32769, 33333, 65537, 100003]
     for Nr in sizes:
         B = 1 if Nr > 20000 else 2
         Nq = int(rng.integers(33, 700))

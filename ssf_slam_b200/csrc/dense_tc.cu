@@ -71,7 +71,18 @@ struct DenseCfg {
     int nd;          // accumulator buffers
     int n_tiles;     // row tiles
     int pd;          // A chunks a producer warp keeps in flight ahead of the one it converts (ring of pd + 1 staging tiles)
+    // division of a row / point number (< 2^31) by the invariant S resp. Nq as multiply-high + add + shift (Granlund-Montgomery):
+    // the rows are 64-bit in the interface, and a 64-bit division is ~70 instructions -- there were six of them per thread per tile
+    unsigned s_mul, s_sh, nq_mul, nq_sh;
 };
+
+__device__ __forceinline__ unsigned dt_fastdiv(unsigned n, unsigned mul, unsigned sh) { return (__umulhi(n, mul) + n) >> sh; }
+static void dt_fastdiv_make(unsigned d, unsigned* mul, unsigned* sh) {   // n / d == (umulhi(n, mul) + n) >> sh for n < 2^31, d >= 1
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    *mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    *sh = l;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
@@ -140,11 +151,11 @@ __device__ __forceinline__ void lds8(const float* p, float (&o)[8]) {
 }
 
 // per-row geometry of a tile
-struct RowCtx {
-    long long row;    // global row (may be >= rows in the last tile)
-    long long rowc;   // clamped
-    long long pt;     // flat point index (row / S)
-    long long srow;   // flat source row b * Nsrc + idx
+struct RowCtx {   // (rows < 2^31: 32-bit indices, widened only when they scale a pointer)
+    unsigned row;     // global row (may be >= rows in the last tile)
+    unsigned rowc;    // clamped
+    unsigned pt;      // flat point index (row / S)
+    unsigned srow;    // flat source row b * Nsrc + idx
     float px, py, pz; // pos_src[srow]
     float qx, qy, qz; // pos_q[pt]
 };
@@ -262,9 +273,9 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
             const uint32_t lbo = (uint32_t)(Nt / 8) * 128;
             const uint64_t lo_off = (uint64_t)(((uint32_t)Nt * KC * 4) >> 4), k_step = (uint64_t)((2 * lbo) >> 4);
             for (int it = 0; it < n_my; ++it) {
-                const int db = it % cfg.nd;
+                const int db = it & (cfg.nd - 1);   // nd is 1 or 2
                 if (it >= cfg.nd) {
-                    ssf_mbar_wait(&d_empty[db], (uint32_t)((it / cfg.nd - 1) & 1));
+                    ssf_mbar_wait(&d_empty[db], (uint32_t)(((it >> (cfg.nd >> 1)) - 1) & 1));
                     tc_fence_after();
                 }
                 const uint32_t d_tmem = tmem + (uint32_t)(db * Nt);
@@ -310,8 +321,9 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
         const bool grouped = a.S > 0 && a.idx != nullptr;
         const bool need_dir = grouped && a.Wd1 != nullptr;
 
-        auto row_of = [&](int it) -> long long { return ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r; };
-        auto clampr = [&](long long row) -> long long { return row < a.rows ? row : a.rows - 1; };
+        const unsigned n_rows = (unsigned)a.rows;
+        auto row_of = [&](int it) -> unsigned { return (blockIdx.x + (unsigned)it * gridDim.x) * 128u + (unsigned)r; };
+        auto clampr = [&](unsigned row) -> unsigned { return row < n_rows ? row : n_rows - 1u; };
         auto load_idx = [&](int it) -> int {   // neighbour index of this thread's row in tile `it`
             if (!grouped || it >= n_my) return 0;
             return __ldg(a.idx + clampr(row_of(it)));
@@ -320,15 +332,14 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
             RowCtx c;
             c.row = row_of(it < n_my ? it : n_my - 1);
             c.rowc = clampr(c.row);
-            c.pt = a.S > 0 ? c.rowc / a.S : 0;
+            c.pt = a.S > 0 ? dt_fastdiv(c.rowc, cfg.s_mul, cfg.s_sh) : 0u;
             c.srow = 0;
             c.px = c.py = c.pz = c.qx = c.qy = c.qz = 0.f;
             if (grouped) {
-                const long long b = c.pt / a.Nq;
-                c.srow = b * a.Nsrc + id;
+                c.srow = dt_fastdiv(c.pt, cfg.nq_mul, cfg.nq_sh) * (unsigned)a.Nsrc + (unsigned)id;
                 if (need_dir) {
-                    const float* ps = a.pos_src + c.srow * 3;
-                    const float* pq = a.pos_q + c.pt * 3;
+                    const float* ps = a.pos_src + (size_t)c.srow * 3u;
+                    const float* pq = a.pos_q + (size_t)c.pt * 3u;
                     c.px = __ldg(ps); c.py = __ldg(ps + 1); c.pz = __ldg(ps + 2);
                     c.qx = __ldg(pq); c.qy = __ldg(pq + 1); c.qz = __ldg(pq + 2);
                 }
@@ -346,12 +357,14 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
         const int total_n = wg < n_my ? ((n_my - wg + NPROD - 1) / NPROD) * nk : 0;
         auto my_of = [&](int t, int id) -> int {   // row of this thread in the source array for the warpgroup's t-th tile
             const int it = wg + t * NPROD;
-            const long long rowc = clampr(row_of(it < n_my ? it : n_my - 1));
+            const unsigned rowc = clampr(row_of(it < n_my ? it : n_my - 1));
             if (a.a_mode == 0) return (int)rowc;
-            const long long pt = rowc / a.S;
-            return (int)((pt / a.Nq) * a.Nsrc + id);
+            const unsigned pt = dt_fastdiv(rowc, cfg.s_mul, cfg.s_sh);
+            return (int)(dt_fastdiv(pt, cfg.nq_mul, cfg.nq_sh) * (unsigned)a.Nsrc + (unsigned)id);
         };
         int pf_n = 0, pf_t = 0, pf_kc = 0;
+        int pf_slot = 0, tk_slot = 0;        // pf_n % D and n % D of the ring, kept as counters (D is a run-time 2 or 3)
+        uint32_t tk_phase = 0;               // (n / D) & 1
         int my_pf = my_of(0, load_idx(wg));
         int idx_nx = load_idx(wg + NPROD);
         const bool tma_g = cfg.tma_g != 0;
@@ -364,7 +377,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                 // tile::gather4 -- no per-lane address arithmetic, no load-store-unit queue slots held while the rows travel
                 if (pf_n < total_n) {
                     const int k0 = pf_kc * KC;
-                    const int slot = pf_n % D;
+                    const int slot = pf_slot;
                     const int g0 = (lane & 7) * 4;
                     const int r0 = __shfl_sync(0xffffffffu, my_pf, g0), r1 = __shfl_sync(0xffffffffu, my_pf, g0 + 1);
                     const int r2 = __shfl_sync(0xffffffffu, my_pf, g0 + 2), r3 = __shfl_sync(0xffffffffu, my_pf, g0 + 3);
@@ -379,6 +392,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                     }
                 }
                 ++pf_n;
+                if (++pf_slot == D) pf_slot = 0;
                 return;
             }
             if (tma_a) {
@@ -388,7 +402,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                     const int it_pf = wg + pf_t * NPROD;
                     const int row0 = (int)(((long long)blockIdx.x + (long long)it_pf * gridDim.x) * 128 + (warp & 3) * 32);
                     if (lane == 0) {
-                        const int slot = pf_n % D;
+                        const int slot = pf_slot;
                         ssf_mbar_expect_tx(&tbar[slot], TMA_TILE_BYTES);
                         if (k0 < a.c1) tma_load_2d(ttile + slot * TMA_TILE_BYTES, &maps.x1, k0, row0, &tbar[slot]);
                         else tma_load_2d(ttile + slot * TMA_TILE_BYTES, &maps.x2, k0 - a.c1, row0, &tbar[slot]);
@@ -399,23 +413,24 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                     }
                 }
                 ++pf_n;
+                if (++pf_slot == D) pf_slot = 0;
                 return;
             }
             if (pf_n < total_n) {
                 const int k0 = pf_kc * KC;
                 const float* base;
-                long long ld;
+                unsigned ld;
                 if (a.a_mode == 0) {
-                    if (k0 < a.c1) { base = a.x1 + k0; ld = a.ld1; } else { base = a.x2 + (k0 - a.c1); ld = a.ld2; }
+                    if (k0 < a.c1) { base = a.x1 + k0; ld = (unsigned)a.ld1; } else { base = a.x2 + (k0 - a.c1); ld = (unsigned)a.ld2; }
                 } else {
                     base = a.G + a.offG + k0;
-                    ld = a.ldG;
+                    ld = (unsigned)a.ldG;
                 }
-                float* dst = stg + (pf_n % D) * (32 * STG_LD) + pc * 4;
+                float* dst = stg + pf_slot * (32 * STG_LD) + pc * 4;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int rrow = __shfl_sync(0xffffffffu, my_pf, j * 4 + rg);
-                    const float* src = base + (long long)rrow * ld + pc * 4;
+                    const unsigned rrow = (unsigned)__shfl_sync(0xffffffffu, my_pf, j * 4 + rg);
+                    const float* src = base + ((size_t)rrow * ld + (unsigned)(pc * 4));   // one 32 x 32 -> 64-bit multiply-add
                     if (a.a_mode == 0) cp_async16_cg(dst + (j * 4 + rg) * STG_LD, src);   // streamed once
                     else cp_async16_ca(dst + (j * 4 + rg) * STG_LD, src);                 // gathered rows are re-used by neighbours
                 }
@@ -427,12 +442,13 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                 }
             }
             ++pf_n;
+            if (++pf_slot == D) pf_slot = 0;
             cp_async_commit();
         };
         auto take_chunk = [&](int n, float (&v)[4][8]) {   // waits for chunk n of the sequence, reads this thread's row
             if (tma_a) {
-                const int slot = n % D;
-                ssf_mbar_wait(&tbar[slot], (uint32_t)((n / D) & 1));
+                const int slot = tk_slot;
+                ssf_mbar_wait(&tbar[slot], tk_phase);
                 const uint8_t* src = ttile + slot * TMA_TILE_BYTES;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -441,15 +457,17 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                     v[q][0] = x.x; v[q][1] = x.y; v[q][2] = x.z; v[q][3] = x.w; v[q][4] = y.x; v[q][5] = y.y; v[q][6] = y.z; v[q][7] = y.w;
                 }
                 __syncwarp();   // the slot is refilled by the tensor-map load issued for chunk n + D in the next step
+                if (++tk_slot == D) { tk_slot = 0; tk_phase ^= 1u; }
                 return;
             }
             if (PD == 1) cp_async_wait<1>();
             else cp_async_wait<2>();
             __syncwarp();
-            const float* src = stg + (n % D) * (32 * STG_LD) + lane * STG_LD;
+            const float* src = stg + tk_slot * (32 * STG_LD) + lane * STG_LD;
 #pragma unroll
             for (int q = 0; q < 4; ++q) lds8(src + q * 8, v[q]);
             __syncwarp();   // the slot is overwritten by the cp.async issued for chunk n + D in the next step
+            if (++tk_slot == D) { tk_slot = 0; tk_phase ^= 1u; }
         };
 
         if (wg < n_my) {
@@ -474,7 +492,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                     const int k0 = kc * KC;
                     if (a.a_mode == 1) {
                         if (a.H != nullptr) {
-                            const float* hs = a.H + cur.pt * a.ldH + a.offH + k0;
+                            const float* hs = a.H + ((size_t)cur.pt * (unsigned)a.ldH + (unsigned)(a.offH + k0));
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 float h[8];
@@ -546,14 +564,14 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
         const int eg = (warp - W_EPI) >> 2;                            // epilogue warpgroup: columns [c_lo, c_hi) of the tile
         const int c_lo = eg * (Nt / NEPI), c_hi = c_lo + Nt / NEPI;
         for (int it = 0; it < n_my; ++it) {
-            const int db = it % cfg.nd;
+            const int db = it & (cfg.nd - 1);   // nd is 1 or 2
             const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r;
             const bool valid = row < a.rows;
             const long long rowc = valid ? row : a.rows - 1;
-            const long long pt = a.S > 0 ? rowc / a.S : 0;
+            const long long pt = a.S > 0 ? (long long)dt_fastdiv((unsigned)rowc, cfg.s_mul, cfg.s_sh) : 0;
             float dx = 0.f, dy = 0.f, dz = 0.f;
             if (need_dir) {
-                const long long b = pt / a.Nq;
+                const long long b = (long long)dt_fastdiv((unsigned)pt, cfg.nq_mul, cfg.nq_sh);
                 const float* ps = a.pos_src + (b * a.Nsrc + __ldg(a.idx + rowc)) * 3;
                 const float* pq = a.pos_q + pt * 3;
                 dx = __ldg(ps) - __ldg(pq);
@@ -561,7 +579,7 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                 dz = __ldg(ps + 2) - __ldg(pq + 2);
             }
             DTRACE(1, 0);   // row setup
-            ssf_mbar_wait(&d_full[db], (uint32_t)((it / cfg.nd) & 1));
+            ssf_mbar_wait(&d_full[db], (uint32_t)((it >> (cfg.nd >> 1)) & 1));
             tc_fence_after();
             DTRACE(1, 1);   // wait for the accumulator
             const uint32_t t_d = tmem + lane_base + (uint32_t)(db * Nt);
@@ -803,7 +821,10 @@ extern "C" int ssf_dense_tc(const ssf_dense_args* args, void* stream) {
     if (a.epi_mode == SSF_EPI_DOT && (a.N > 256 || a.wvec == nullptr)) return ssf_arg_error("dense_tc: dot epilogue needs N <= 256 and wvec");
     if ((a.Wd1 != nullptr || a.Wd2 != nullptr) && (a.pos_src == nullptr || a.pos_q == nullptr || a.idx == nullptr))
         return ssf_arg_error("dense_tc: direction term needs pos_src, pos_q, idx");
+    if (a.rows >= (1ll << 31)) return ssf_arg_error("dense_tc: at most 2^31 - 1 rows");
     DenseCfg cfg;
+    dt_fastdiv_make(a.S > 0 ? (unsigned)a.S : 1u, &cfg.s_mul, &cfg.s_sh);
+    dt_fastdiv_make(a.Nq > 0 ? (unsigned)a.Nq : 1u, &cfg.nq_mul, &cfg.nq_sh);
     cfg.Nt = a.N < 256 ? a.N : 256;
     cfg.nk = a.K / KC;
     const size_t wchunk = (size_t)cfg.Nt * KC * 4 * 2;

@@ -44,9 +44,11 @@ struct CvTcArgs {
     const uint8_t* wblob; const float* params;
     const float* xyz1; const float* xyz2; const int* idx; const int* idxw;
     int B, N1, N2, tiles_per_cloud, n_tiles;
+    unsigned tpc_mul, tpc_sh;   // tile / tiles_per_cloud == (umulhi(tile, tpc_mul) + tile) >> tpc_sh (tile < 2^31; a division is ~25 instructions, four per thread per tile)
     float* cost_fwd; float* cost_fwd_cm; float* gw; float* Cw;
 };
 
+__device__ __forceinline__ int cv_div(int tile, const CvTcArgs& a) { return (int)((__umulhi((unsigned)tile, a.tpc_mul) + (unsigned)tile) >> a.tpc_sh); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
 }
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
         // neighbour index of this thread's row, fetched one tile ahead
         auto tile_qrow = [&](int it_) -> size_t {
             const int tile_ = (int)blockIdx.x + it_ * (int)gridDim.x;
-            const int b_ = tile_ / a.tiles_per_cloud, n_ = (tile_ % a.tiles_per_cloud) * 8 + p;
+            const int b_ = cv_div(tile_, a), n_ = (tile_ - b_ * a.tiles_per_cloud) * 8 + p;
             return (size_t)b_ * a.N1 + (n_ < a.N1 ? n_ : a.N1 - 1);
         };
         int id_next = n_my > 0 ? __ldg(idx_br + tile_qrow(0) * 16 + s) : 0;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
         // cp.async: issued as soon as the sub-tile is free in the previous tile, so the gather latency hides behind E2..E6
         auto gather_issue = [&](int it_, int id_) {
             const int tile_ = (int)blockIdx.x + it_ * (int)gridDim.x;
-            const int b_ = tile_ / a.tiles_per_cloud;
+            const int b_ = cv_div(tile_, a);
             const float* gbase = a.Gab + (size_t)b_ * a.N2 * (2 * CM) + br * CM + c0 + pc * 4;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
         // Hab rows of the 8 points of a tile: 256 float4, one per thread of warps 0-7; tile `it` sits in buffer it & 1
         auto hab_load = [&](int it_) -> float4 {
             const int tile_ = (int)blockIdx.x + it_ * (int)gridDim.x;
-            const int b_ = tile_ / a.tiles_per_cloud, n_ = (tile_ % a.tiles_per_cloud) * 8 + (tid >> 5);
+            const int b_ = cv_div(tile_, a), n_ = (tile_ - b_ * a.tiles_per_cloud) * 8 + (tid >> 5);
             return __ldg(reinterpret_cast<const float4*>(a.Hab + ((size_t)b_ * a.N1 + (n_ < a.N1 ? n_ : a.N1 - 1)) * (2 * CM)) + (tid & 31));
         };
         if (tid < 256 && n_my > 0) *reinterpret_cast<float4*>(sHab + tid * 4) = hab_load(0);
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cost_volume_tc64_kernel(CvTcArgs 
         for (int it = 0; it < n_my; ++it) {
             TRACE(br, 0);
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const int b = tile / a.tiles_per_cloud;
-            const int n0 = (tile % a.tiles_per_cloud) * 8;
+            const int b = cv_div(tile, a);
+            const int n0 = (tile - b * a.tiles_per_cloud) * 8;
             const bool valid = n0 + p < a.N1;
             const int n = valid ? n0 + p : a.N1 - 1;
             const size_t qrow = (size_t)b * a.N1 + n;
@@ -692,6 +694,13 @@ extern "C" int ssf_cost_volume_tc(const float* Gab, const float* Hab, const floa
     a.xyz1 = xyz1; a.xyz2 = xyz2; a.idx = idx; a.idxw = idxw;
     a.B = B; a.N1 = N1; a.N2 = N2;
     a.tiles_per_cloud = (N1 + 7) / 8;
+    {
+        const unsigned d = (unsigned)a.tiles_per_cloud;
+        unsigned l = 0;
+        while ((1ull << l) < d) ++l;
+        a.tpc_mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+        a.tpc_sh = l;
+    }
     a.n_tiles = a.tiles_per_cloud * B;
     a.cost_fwd = cost_fwd; a.cost_fwd_cm = cost_fwd_cm; a.gw = gw; a.Cw = Cw;
     cudaError_t e = cudaFuncSetAttribute(cost_volume_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_TC_SMEM);

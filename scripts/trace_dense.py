@@ -27,6 +27,7 @@ for rows, K, N in shapes:
     print("rows=%d K=%d N=%d: %d tiles, %d chunks in CTA 0" % (rows, K, N, tiles, chunks))
     names = ["loop rest", "issue cp.async", "wait+read chunk", "first-layer math", "wait A stage", "split + st issue", "wait::st", "", "", "", "", "", "", "", "", "arrive"]
     print("  producer (cycles per chunk): " + "  ".join("%s=%.0f" % (names[i], t[i] / chunks) for i in (0, 1, 2, 3, 4, 5, 6, 15)))
+    print("    inside the prefetch issue (tensor-map path): address arithmetic=%.0f  expect_tx=%.0f  cp.async.bulk.tensor issue=%.0f" % tuple(t[i] / chunks for i in (7, 8, 9)))
     print("  epilogue (cycles per tile):  setup=%.0f  wait accumulator=%.0f  column loop=%.0f  arrive=%.0f" %
           tuple(t[16 + i] / tiles / max(1, N // 256) for i in (0, 1, 2, 15)))
     print("    column loop per tile: tail=%.0f  tcgen05.ld+wait=%.0f  math=%.0f  staging stores=%.0f  row-segment stores=%.0f" %

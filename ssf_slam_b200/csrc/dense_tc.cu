@@ -401,11 +401,14 @@ dense_tc_kernel(ssf_dense_args a, DenseCfg cfg, const __grid_constant__ DenseMap
                     const int k0 = pf_kc * KC;
                     const int it_pf = wg + pf_t * NPROD;
                     const int row0 = (int)(((long long)blockIdx.x + (long long)it_pf * gridDim.x) * 128 + (warp & 3) * 32);
+                    DTRACE(0, 7);    // (trace build) address arithmetic of the prefetch
                     if (lane == 0) {
                         const int slot = pf_slot;
                         ssf_mbar_expect_tx(&tbar[slot], TMA_TILE_BYTES);
+                        DTRACE(0, 8);    // expect_tx
                         if (k0 < a.c1) tma_load_2d(ttile + slot * TMA_TILE_BYTES, &maps.x1, k0, row0, &tbar[slot]);
                         else tma_load_2d(ttile + slot * TMA_TILE_BYTES, &maps.x2, k0 - a.c1, row0, &tbar[slot]);
+                        DTRACE(0, 9);    // tensor-map load issue
                     }
                     if (++pf_kc == nk) {
                         pf_kc = 0;

@@ -480,3 +480,23 @@ def test_interpolate_kernel_variants_are_bit_identical(C, k, mode):
         got = F_.interpolate(q, sp, val, idx, mode=1, clampv=10.0, k=k)
         unclamped = F_.interpolate(q, sp, wide, idx, mode=0, clampv=3.0e38, k=k)[..., :3]
         assert torch.equal(got, (q - unclamped).clamp(-10.0, 10.0))
+
+
+@pytest.mark.parametrize("m,P", [(128, 1000), (256, 893), (512, 301), (128, 7)])
+def test_attention_mix_persistent_kernel(m, P):
+    """The S x S cross attention of the wide cost volumes (cv_parts.cu attention_mix_kernel; soflow.py:420-422,453-458) against
+    a plain PyTorch fp32 statement of the same formula; P is chosen so that the persistent CTAs wrap around several times and
+    the last round is ragged (both shared-memory buffers and both mbarrier phases are exercised)."""
+    from ssf_slam_b200 import functional as F_
+    g = torch.Generator().manual_seed(m + P)
+    A = (torch.randn(P, 16, m, generator=g) * 0.5).cuda()
+    Aw = (torch.randn(P, 16, m, generator=g) * 0.5).cuda()
+    Amix, Awmix = F_.attention_mix(A, Aw)
+    S = torch.einsum("pic,pjc->pij", A.double(), Aw.double())
+    Q = torch.softmax(S, dim=1) * torch.softmax(S, dim=2)
+    want_a = A.double() + torch.einsum("pij,pjc->pic", Q, Aw.double())
+    want_w = Aw.double() + torch.einsum("pij,pic->pjc", Q, A.double())
+    assert float((Amix.double() - want_a).abs().max()) < 2e-5
+    assert float((Awmix.double() - want_w).abs().max()) < 2e-5
+    a2, w2 = F_.attention_mix(A, Aw)          # deterministic
+    assert torch.equal(a2, Amix) and torch.equal(w2, Awmix)

@@ -195,11 +195,107 @@ __global__ void __launch_bounds__(256) linear_kernel(LinearArgs a) {
     }
 }
 
+// Narrow layers, where the 64 x 64 tile above wastes most of its lanes: same sums in the same order (one fmaf chain over
+// ascending k from 0, then bias, activation, clamp, residual, clamp), so bit-identical to linear_kernel.
+//   * few outputs (cout <= 4: the flow heads, 64-256 -> 3): lane = row; a warp reads 32 rows x 32 k with coalesced 128-byte loads,
+//     transposes them through a padded shared-memory tile and every lane runs its row's chain; the layer reads its input once
+//     at memory speed instead of spending 15 of 16 column-threads on padding (level 0: 173 -> ~30 us for 524288 rows)
+//   * few inputs (K <= 4: the first per-point layer, 3 -> 32): thread = (row, 4 outputs), coalesced 16-byte stores
+__global__ void __launch_bounds__(256) linear_narrow_out_kernel(LinearArgs a) {
+    __shared__ float sT[8][32][33];
+    __shared__ float sW[512 * 4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.c1;
+    for (int i = tid; i < K * 4; i += 256) {
+        const int k = i >> 2, c = i & 3;
+        sW[i] = c < a.cout ? __ldg(a.Wt + (size_t)(a.w_off1 + k) * a.ldw + c) : 0.f;
+    }
+    __syncthreads();
+    const long long r0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    if (r0 >= a.rows) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kn = K - k0 < 32 ? K - k0 : 32;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const long long row = r0 + j;
+            sT[warp][j][lane] = (row < a.rows && lane < kn) ? __ldg(a.x1 + (size_t)row * a.ld1 + k0 + lane) : 0.f;
+        }
+        __syncwarp();
+        for (int kk = 0; kk < kn; ++kk) {
+            const float xv = sT[warp][lane][kk];
+            const float4 w = *reinterpret_cast<const float4*>(sW + (k0 + kk) * 4);
+            acc[0] = fmaf(xv, w.x, acc[0]);
+            acc[1] = fmaf(xv, w.y, acc[1]);
+            acc[2] = fmaf(xv, w.z, acc[2]);
+            acc[3] = fmaf(xv, w.w, acc[3]);
+        }
+        __syncwarp();
+    }
+    const long long row = r0 + lane;
+    if (row >= a.rows) return;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (c >= a.cout) continue;
+        float v = acc[c] + (a.bias ? __ldg(a.bias + c) : 0.f);
+        v = act_fn(v, a.act);
+        if (a.clamp1 > 0.f) v = fminf(fmaxf(v, -a.clamp1), a.clamp1);
+        if (a.add != nullptr) v += __ldg(a.add + (size_t)row * a.ld_add + c);
+        if (a.clamp2 > 0.f) v = fminf(fmaxf(v, -a.clamp2), a.clamp2);
+        a.y[(size_t)row * a.ldy + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) linear_narrow_in_kernel(LinearArgs a, int q4) {   // q4 = cout / 4
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long row = t / q4;
+    if (row >= a.rows) return;
+    const int c = (int)(t - row * q4) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < a.c1) x[k] = __ldg(a.x1 + (size_t)row * a.ld1 + k);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < a.c1) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(a.Wt + (size_t)(a.w_off1 + k) * a.ldw + c));
+            acc[0] = fmaf(x[k], w.x, acc[0]);
+            acc[1] = fmaf(x[k], w.y, acc[1]);
+            acc[2] = fmaf(x[k], w.z, acc[2]);
+            acc[3] = fmaf(x[k], w.w, acc[3]);
+        }
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[q] = acc[q] + (a.bias ? __ldg(a.bias + c + q) : 0.f);
+        v[q] = act_fn(v[q], a.act);
+        if (a.clamp1 > 0.f) v[q] = fminf(fmaxf(v[q], -a.clamp1), a.clamp1);
+        if (a.add != nullptr) v[q] += __ldg(a.add + (size_t)row * a.ld_add + c + q);
+        if (a.clamp2 > 0.f) v[q] = fminf(fmaxf(v[q], -a.clamp2), a.clamp2);
+    }
+    *reinterpret_cast<float4*>(a.y + (size_t)row * a.ldy + c) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 extern "C" int ssf_linear(const float* x1, int c1, int ld1, const float* x2, int c2, int ld2, const float* Wt, int ldw,
                           int w_off1, int w_off2, const float* bias, int rows, int cout, int act, float clamp1,
                           const float* add, int ld_add, float clamp2, float* y, int ldy, void* stream) {
     if (rows <= 0 || cout <= 0 || c1 <= 0) return ssf_arg_error("linear: empty input");
     LinearArgs a = {x1, c1, ld1, x2, x2 ? c2 : 0, ld2, Wt, ldw, w_off1, w_off2, bias, rows, cout, act, clamp1, add, ld_add, clamp2, y, ldy};
+    if (x2 == nullptr && cout <= 4 && c1 <= 512 && c1 >= 16) {
+        linear_narrow_out_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
+    if (x2 == nullptr && c1 <= 4 && cout % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0 &&
+        ((reinterpret_cast<uintptr_t>(Wt) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        const int q4 = cout / 4;
+        linear_narrow_in_kernel<<<(unsigned)(((long long)rows * q4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, q4);
+        ssf_count_launch();
+        SSF_LAUNCH_CHECK();
+        return SSF_OK;
+    }
     dim3 grid((rows + 63) / 64, (cout + 63) / 64);
     linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     ssf_count_launch();

@@ -500,3 +500,24 @@ def test_attention_mix_persistent_kernel(m, P):
     assert float((Awmix.double() - want_w).abs().max()) < 2e-5
     a2, w2 = F_.attention_mix(A, Aw)          # deterministic
     assert torch.equal(a2, Amix) and torch.equal(w2, Awmix)
+
+
+@pytest.mark.parametrize("rows,K,cout", [(5000, 64, 3), (777, 256, 4), (33, 128, 3), (100000, 96, 1), (4099, 3, 32), (1000, 3, 64), (513, 4, 32)])
+def test_linear_narrow_kernels_equal_the_tiled_kernel(rows, K, cout):
+    """Flow heads (cout <= 4) and the first per-point layer (K <= 4) run dedicated kernels (layers.cu linear_narrow_*) with the
+    same fmaf chain as the 64 x 64 tiled kernel.  A second, all-zero input block forces the tiled kernel (fmaf(0, w, acc) == acc),
+    so both results must be bit-identical -- bias, activation, both clamps and the residual included."""
+    from ssf_slam_b200 import functional as F_
+    g = torch.Generator().manual_seed(rows + K + cout)
+    x = torch.randn(rows, K, generator=g).cuda()
+    Wt = (torch.randn(K + 16, cout, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    add = (torch.randn(rows, cout, generator=g) * 30).cuda()
+    z = torch.zeros(rows, 16, device="cuda")
+    for kw in (dict(bias=b, act=2), dict(bias=b, clamp1=1.5, add=add, clamp2=40.0), dict()):
+        got = F_.linear(x, Wt, cout, 0, **kw)
+        ref = F_.linear(x, Wt, cout, 0, z, K, **kw)
+        assert torch.equal(got, ref), kw.keys()
+    want = x.double() @ Wt[:K].double() + b.double()
+    got = F_.linear(x, Wt, cout, 0, bias=b)
+    assert float((got.double() - want).abs().max()) < 1e-4

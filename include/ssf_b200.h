@@ -45,7 +45,7 @@ int ssf_knn(int k, const float* query, const float* ref, int B, int Nq, int Nr, 
 int ssf_knn_offset(int k, const float* query, const float* query_add, const float* ref, int B, int Nq, int Nr,
                    float* dist, int* idx, void* stream);
 
-/* Same result as ssf_knn_offset, bit for bit, through a spatial index: `build` Morton-sorts each reference cloud into
+/* Same result as ssf_knn_offset, bit for bit, through a spatial index: `build` sorts each reference cloud along a Hilbert curve (isotropic 10-bit cells) into
  * blocks of 32 points with bounding boxes (workspace of ssf_knn_blocks_workspace_floats(B,Nr) floats, Nr <= 131072; above
  * 16384 points the sort is a global-memory radix sort and super-blocks of 32 blocks add a second level),
  * `search` walks the blocks nearest-first and stops when no remaining box can hold a closer point. */

@@ -147,7 +147,7 @@ def fps(xyz, npoint):
     return out
 
 
-# reference clouds at least this large go through the Morton-block search (csrc/knn_blocks.cu); smaller ones through the
+# reference clouds at least this large go through the Hilbert-ordered block search (csrc/knn_blocks.cu); smaller ones through the
 # brute-force scan.  Both return identical indices.
 KNN_BLOCKS_MIN_REF = 256   # (measured at 128 clouds: 512 queries in 256 points 0.098 ms scanned, 0.064 ms with index build + search)
 KNN_BLOCKS_MAX_REF = 131072   # one-level index up to 16384 points, two-level (super-blocks) above

@@ -57,7 +57,7 @@ INDEX_MAX_POINTS = 131072
 @torch.no_grad()
 def build_index(xyz):
     """Spatial index of the clouds xyz f32 [B,N,3] (N <= 131072) for ``knn(..., index=)`` and ``ball_query(..., index=)``:
-    Morton-sorted blocks of 32 points with bounding boxes (csrc/knn_blocks.cu).  Extension of the reference API: it lets
+    Hilbert-curve-sorted blocks of 32 points with bounding boxes (csrc/knn_blocks.cu).  Extension of the reference API: it lets
     several searches in the same cloud (a radius sweep, kNN + ball query) share one build; every search returns exactly what
     the un-indexed operator returns."""
     nat.require_device()
@@ -83,7 +83,7 @@ def knn(k, unknown, known, offset=None, index=None):
     off = None if offset is None else _f32(offset)
     L = nat.lib()
     if index is not None or F_.KNN_BLOCKS_MIN_REF <= Nr <= 16384 or (16384 < Nr <= INDEX_MAX_POINTS and B * Nq > 32768):
-        # Morton-block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster; above 16384
+        # block search (csrc/knn_blocks.cu): bit-identical to the brute-force scan, several times faster; above 16384
         # reference points a two-level index (radix-sorted build, super-blocks of 32 blocks)
         ws = index if index is not None else build_index(known)
         nat.check(L.ssf_knn_blocks_search(int(k), nat.ptr(unknown), nat.ptr(off), nat.ptr(ws), B, Nq, Nr, nat.ptr(dist),

@@ -72,7 +72,7 @@ def test_fps(pu, N, npoint):
     assert np.array_equal(got, po.c_fps(x, npoint))
 
 
-@pytest.mark.parametrize("case", ["n2049", "n4097", "all_equal", "planar", "line", "clusters", "select_all", "lidar", "tiny_far"])
+@pytest.mark.parametrize("case", ["n2049", "n4097", "all_equal", "planar", "line", "clusters", "select_all", "more_than_all", "lidar", "tiny_far"])
 def test_fps_pruned_kernel_edge_cases(pu, case):
     """The spatially pruned sampler (2048 < N <= 8192: Morton rows + box bound, point_ops.cu fps_pruned_kernel) must stay
     bit-identical to the plain scan of the oracle where its machinery is stressed: nearly empty padded rows, zero extents,
@@ -98,6 +98,9 @@ def test_fps_pruned_kernel_edge_cases(pu, case):
     elif case == "select_all":
         x = _cloud(14, 1, 2500)
         npoint = 2500
+    elif case == "more_than_all":
+        x = _cloud(15, 2, 3000)
+        npoint = 3100         # every minimum is 0 after 3000 samples: index 0 again and again, as the plain scan does
     elif case == "lidar":
         from ssf_slam_b200 import synth
         x = np.stack([it["pos1"] for it in synth.make_sequence(77, 2, 8192)]).astype(np.float32)

@@ -29,7 +29,9 @@ int ssf_require_device(void);                 /* non-zero unless the current dev
 /* ---- B-op: lib.pointnet2_utils drop-ins (reference layouts) ---- */
 
 /* furthest_point_sample(xyz[B,N,3], npoint) -> idx[B,npoint]; call site ASF/utils/utils.py:226.
- * First index 0, running min initialised 1e10, argmax ties -> lowest index. N <= 131072. */
+ * First index 0, running min initialised 1e10, argmax ties -> lowest index. N <= 131072.
+ * 2048 < N <= 8192 runs an exactly pruned variant (Hilbert-sorted rows with box bounds; same indices bit for bit; the
+ * environment variable SSF_FPS_PRUNE=0 selects the plain scan for comparisons), N > 8192 a thread-block cluster per cloud. */
 int ssf_furthest_point_sample(const float* xyz, int B, int N, int npoint, int* idx, void* stream);
 
 /* gather_operation(features cm[B,C,N], idx[B,M]) -> cm[B,C,M]; ASF/utils/utils.py:228 */

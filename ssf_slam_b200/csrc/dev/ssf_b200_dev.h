@@ -20,6 +20,10 @@ int ssf_tc_gemm_test(const float* X, const float* Whi_img, const float* Wlo_img,
  * TMEM (mode 0) or shared memory (mode 1), acc_bufs accumulators round-robin; out[0] = total cycles, out[1] = issue cycles */
 int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long long* out, void* stream);
 
+/* host evaluation of the curve key the spatial indices sort by (ssf_common.cuh ssf_hilbert30; no GPU needed): n cells with
+ * 10-bit coordinates -> 30-bit keys */
+int ssf_dev_hilbert30(const unsigned* xyz, int n, unsigned* key);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,3 +182,9 @@ extern "C" int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long lon
     SSF_LAUNCH_CHECK();
     return SSF_OK;
 }
+
+// host evaluation of the Hilbert key (regression test of the curve: tests/test_host.py)
+extern "C" int ssf_dev_hilbert30(const unsigned* xyz, int n, unsigned* key) {
+    for (int i = 0; i < n; ++i) key[i] = ssf_hilbert30(xyz[3 * i] & 1023u, xyz[3 * i + 1] & 1023u, xyz[3 * i + 2] & 1023u);
+    return 0;
+}

@@ -41,14 +41,14 @@ __device__ __forceinline__ float ssf_sqdist(float ax, float ay, float az, float 
 // Sorting a cloud by it makes runs of consecutive points spatially compact; every index built on such runs (kNN / ball-query
 // blocks, the pruned sampler's rows) is exact for ANY order, the curve only decides how many blocks a query has to open:
 // on LiDAR sweeps 4.5 blocks of 32 intersect a 16-NN ball with Hilbert order, 6.2 with Morton (Z) order of the same cells.
-__device__ __forceinline__ unsigned ssf_spread10(unsigned v) {   // 10 bits -> every third bit
+__host__ __device__ __forceinline__ unsigned ssf_spread10(unsigned v) {   // 10 bits -> every third bit
     v = (v | (v << 16)) & 0x030000FFu;
     v = (v | (v << 8)) & 0x0300F00Fu;
     v = (v | (v << 4)) & 0x030C30C3u;
     v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
-__device__ __forceinline__ unsigned ssf_hilbert30(unsigned x, unsigned y, unsigned z) {
+__host__ __device__ __forceinline__ unsigned ssf_hilbert30(unsigned x, unsigned y, unsigned z) {
     unsigned X[3] = {x, y, z};
 #pragma unroll
     for (unsigned Q = 512u; Q > 1u; Q >>= 1) {

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssf_b200.so")
 
 _P, _I, _F, _U64, _I64, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_longlong, ctypes.c_double
-_CODES = {"p": _P, "i": _I, "f": _F, "Q": _U64, "q": _I64, "d": _D, "H": ctypes.c_void_p}   # "H": host pointer (no device bookkeeping)
+_CODES = {"p": _P, "i": _I, "f": _F, "Q": _U64, "q": _I64, "d": _D, "H": ctypes.c_void_p, "I": ctypes.c_uint}   # "H": host pointer (no device bookkeeping)
 
 # name -> (argument codes, restype); mirrors include/ssf_b200.h one to one
 SIGNATURES = {
@@ -73,6 +73,7 @@ DEV_SIGNATURES = {
     "ssf_tc_gemm_test": ("pppiiiipp", _I),
     "ssf_tc_mma_rate": ("iiiipp", _I),
     "ssf_dev_hilbert30": ("HiH", _I),
+    "ssf_dev_fastdiv": ("HiIH", _I),
 }
 
 

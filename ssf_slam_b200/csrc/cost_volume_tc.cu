@@ -48,7 +48,7 @@ struct CvTcArgs {
     float* cost_fwd; float* cost_fwd_cm; float* gw; float* Cw;
 };
 
-__device__ __forceinline__ int cv_div(int tile, const CvTcArgs& a) { return (int)((__umulhi((unsigned)tile, a.tpc_mul) + (unsigned)tile) >> a.tpc_sh); }
+__device__ __forceinline__ int cv_div(int tile, const CvTcArgs& a) { return (int)ssf_fastdiv((unsigned)tile, a.tpc_mul, a.tpc_sh); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssf_smem_u32(bar)) : "memory");
 }
@@ -695,11 +695,9 @@ extern "C" int ssf_cost_volume_tc(const float* Gab, const float* Hab, const floa
     a.B = B; a.N1 = N1; a.N2 = N2;
     a.tiles_per_cloud = (N1 + 7) / 8;
     {
-        const unsigned d = (unsigned)a.tiles_per_cloud;
-        unsigned l = 0;
-        while ((1ull << l) < d) ++l;
-        a.tpc_mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-        a.tpc_sh = l;
+        const SsfFastDiv f = ssf_fastdiv_make((unsigned)a.tiles_per_cloud);
+        a.tpc_mul = f.mul;
+        a.tpc_sh = f.sh;
     }
     a.n_tiles = a.tiles_per_cloud * B;
     a.cost_fwd = cost_fwd; a.cost_fwd_cm = cost_fwd_cm; a.gw = gw; a.Cw = Cw;

@@ -76,12 +76,11 @@ struct DenseCfg {
     unsigned s_mul, s_sh, nq_mul, nq_sh;
 };
 
-__device__ __forceinline__ unsigned dt_fastdiv(unsigned n, unsigned mul, unsigned sh) { return (__umulhi(n, mul) + n) >> sh; }
-static void dt_fastdiv_make(unsigned d, unsigned* mul, unsigned* sh) {   // n / d == (umulhi(n, mul) + n) >> sh for n < 2^31, d >= 1
-    unsigned l = 0;
-    while ((1ull << l) < d) ++l;
-    *mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-    *sh = l;
+__device__ __forceinline__ unsigned dt_fastdiv(unsigned n, unsigned mul, unsigned sh) { return ssf_fastdiv(n, mul, sh); }
+static void dt_fastdiv_make(unsigned d, unsigned* mul, unsigned* sh) {
+    const SsfFastDiv f = ssf_fastdiv_make(d);
+    *mul = f.mul;
+    *sh = f.sh;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -24,6 +24,9 @@ int ssf_tc_mma_rate(int N, int mode, int reps, int acc_bufs, long long* out, voi
  * 10-bit coordinates -> 30-bit keys */
 int ssf_dev_hilbert30(const unsigned* xyz, int n, unsigned* key);
 
+/* host evaluation of the invariant division of the persistent kernels (ssf_common.cuh ssf_fastdiv): q[i] = n[i] / d, n[i] < 2^31 */
+int ssf_dev_fastdiv(const unsigned* n, int count, unsigned d, unsigned* q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,3 +188,11 @@ extern "C" int ssf_dev_hilbert30(const unsigned* xyz, int n, unsigned* key) {
     for (int i = 0; i < n; ++i) key[i] = ssf_hilbert30(xyz[3 * i] & 1023u, xyz[3 * i + 1] & 1023u, xyz[3 * i + 2] & 1023u);
     return 0;
 }
+
+// host evaluation of the invariant division used by the persistent kernels: q[i] = n[i] / d through ssf_fastdiv
+extern "C" int ssf_dev_fastdiv(const unsigned* n, int count, unsigned d, unsigned* q) {
+    if (d == 0) return 1;
+    const SsfFastDiv f = ssf_fastdiv_make(d);
+    for (int i = 0; i < count; ++i) q[i] = ssf_fastdiv(n[i], f.mul, f.sh);
+    return 0;
+}

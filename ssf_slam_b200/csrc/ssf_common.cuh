@@ -37,6 +37,28 @@ __device__ __forceinline__ float ssf_sqdist(float ax, float ay, float az, float 
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Division of n < 2^31 by a run-time invariant d >= 1 as multiply-high + add + shift (Granlund-Montgomery):
+// n / d == (umulhi(n, mul) + n) >> sh with sh = ceil(log2 d), mul = floor(2^32 (2^sh - d) / d) + 1.  A 32-bit division is ~25
+// instructions on the device and a 64-bit one ~70; the persistent tensor-core kernels did several per thread per tile.
+struct SsfFastDiv {
+    unsigned mul, sh;
+};
+static inline SsfFastDiv ssf_fastdiv_make(unsigned d) {
+    SsfFastDiv f;
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    f.mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.sh = l;
+    return f;
+}
+__host__ __device__ __forceinline__ unsigned ssf_fastdiv(unsigned n, unsigned mul, unsigned sh) {
+#ifdef __CUDA_ARCH__
+    return (__umulhi(n, mul) + n) >> sh;
+#else
+    return (unsigned)((((unsigned long long)n * mul) >> 32) + n) >> sh;
+#endif
+}
+
 // 30-bit Hilbert-curve key of a point quantised to 10 bits per axis (Skilling's transpose algorithm, then bit interleave).
 // Sorting a cloud by it makes runs of consecutive points spatially compact; every index built on such runs (kNN / ball-query
 // blocks, the pruned sampler's rows) is exact for ANY order, the curve only decides how many blocks a query has to open:

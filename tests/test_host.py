@@ -296,3 +296,50 @@ def test_hilbert_key_is_a_hilbert_curve():
     rc = nat.dev_lib().ssf_dev_hilbert30(q.ctypes.data_as(ctypes.c_void_p), len(q), key.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0
     assert np.array_equal(key.astype(np.int64), _hilbert_keys_numpy(q.astype(np.int64), 10))
+
+
+def test_invariant_division_matches_integer_division():
+    """The persistent tensor-core kernels map rows to points / clouds with ssf_fastdiv (multiply-high + add + shift,
+    ssf_common.cuh) instead of integer divisions; a wrong quotient would silently gather the wrong rows.  Host evaluation through
+    the developer library: every n < 2^31 class that matters (0, d - 1, d, multiples +- 1, 2^31 - 1, random) for divisors that
+    occur (S = 8, 16; Nq = 128 .. 65536; tiles per cloud) and awkward ones (1, 3, primes, 2^k +- 1, > 2^20)."""
+    import ctypes
+    from ssf_slam_b200 import _native as nat
+    rng = np.random.default_rng(9)
+    divisors = [1, 2, 3, 5, 7, 8, 16, 17, 31, 32, 33, 100, 127, 128, 129, 256, 511, 512, 1000, 1024, 2047, 2048, 4096, 8191, 8192,
+                16384, 65535, 65536, 65537, 100003, (1 << 20) + 7, (1 << 24) - 1, (1 << 30) + 1, (1 << 31) - 1]
+    for d in divisors:
+        n = np.concatenate([np.array([0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - 2], np.int64),
+                            (rng.integers(0, ((1 << 31) - 1) // d + 1, 2000) * d + rng.integers(-1, 2, 2000)),
+                            rng.integers(0, 1 << 31, 20000)])
+        n = np.clip(n, 0, (1 << 31) - 1).astype(np.uint32)
+        q = np.zeros(len(n), np.uint32)
+        assert nat.dev_lib().ssf_dev_fastdiv(n.ctypes.data_as(ctypes.c_void_p), len(n), d, q.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(q.astype(np.int64), n.astype(np.int64) // d), d
+
+
+def test_box_bound_never_exceeds_the_rounded_distance():
+    """Exactness argument of every spatially pruned kernel (block kNN, indexed ball query, pruned sampler): the box bound is
+    computed with the same rounded fp32 operations as the distance -- gap = max(0, lo - q, q - hi) per axis, then
+    ((gx*gx) + (gy*gy)) + (gz*gz) -- and each of them is monotone, so bound <= distance of every point inside the box holds in
+    floating point, not only in exact arithmetic.  Checked op by op in float32 on random boxes, inside points and queries over
+    twelve orders of magnitude, plus points on the faces and queries inside the box."""
+    rng = np.random.default_rng(17)
+    f = np.float32
+    n = 400000
+    scale = (10.0 ** rng.uniform(-6, 6, (n, 1))).astype(f)
+    a, b = (rng.standard_normal((n, 3)).astype(f) * scale), (rng.standard_normal((n, 3)).astype(f) * scale)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    t = rng.uniform(0, 1, (n, 3)).astype(f)
+    t[: n // 4] = np.round(t[: n // 4])                        # points on faces / corners
+    p = np.minimum(np.maximum(lo + (hi - lo) * t, lo), hi)     # inside the box (clamped after rounding)
+    q = rng.standard_normal((n, 3)).astype(f) * scale * f(3)
+    q[n // 2: n // 2 + n // 8] = p[n // 2: n // 2 + n // 8]    # queries inside the box: bound must be exactly 0 <= d
+    d3 = (p - q).astype(f)
+    dist = ((d3[:, 0] * d3[:, 0]).astype(f) + (d3[:, 1] * d3[:, 1]).astype(f)).astype(f)
+    dist = (dist + (d3[:, 2] * d3[:, 2]).astype(f)).astype(f)
+    g = np.maximum(f(0), np.maximum((lo - q).astype(f), (q - hi).astype(f))).astype(f)
+    bound = ((g[:, 0] * g[:, 0]).astype(f) + (g[:, 1] * g[:, 1]).astype(f)).astype(f)
+    bound = (bound + (g[:, 2] * g[:, 2]).astype(f)).astype(f)
+    assert np.all(bound <= dist)
+    assert np.all(bound[n // 2: n // 2 + n // 8] == 0)

@@ -343,3 +343,49 @@ def test_box_bound_never_exceeds_the_rounded_distance():
     bound = (bound + (g[:, 2] * g[:, 2]).astype(f)).astype(f)
     assert np.all(bound <= dist)
     assert np.all(bound[n // 2: n // 2 + n // 8] == 0)
+
+
+def test_pruned_sampling_rule_is_exact_numpy_model():
+    """Algorithm-level check (no GPU) of the pruned furthest point sampler (point_ops.cu fps_pruned_kernel): rows of 32 points of
+    an arbitrary spatial order, a row is updated only when the fp32 box bound to the new sample is below the row's largest
+    running minimum, the arg-max takes the lowest ORIGINAL index among equal maxima.  The NumPy model of that rule must select
+    the same indices as the plain scan of the C oracle -- on a cloud with duplicates and a lattice (massive ties)."""
+    from oracle import point_ops as po
+    from ssf_slam_b200 import synth
+    f = np.float32
+    rng = np.random.default_rng(3)
+    clouds = [synth.make_sequence(11, 1, 8192)[0]["pos1"][:3000].astype(f), np.round(rng.standard_normal((2500, 3)) * 3).astype(f)]
+    clouds[0][100:140] = clouds[0][:40]
+    for x in clouds:
+        N, npoint = len(x), 300
+        order = np.lexsort((np.arange(N), x[:, 1], x[:, 0]))          # any order is exact; this one is merely spatial-ish
+        pad = (-N) % 32
+        ids = np.concatenate([order, np.full(pad, N)]).reshape(-1, 32)
+        xs = np.concatenate([x[order], np.zeros((pad, 3), f)]).reshape(-1, 32, 3)
+        ok = ids < N
+        lo = np.where(ok[..., None], xs, np.inf).min(1).astype(f)
+        hi = np.where(ok[..., None], xs, -np.inf).max(1).astype(f)
+        md = np.full(ids.shape, 1e10, f)
+        submax = np.where(ok.any(1), f(1e10), f(0))
+        subidx = np.where(ok, ids, 1 << 30).min(1)
+        last, sel, skipped = 0, [], 0
+        for it in range(npoint):
+            sel.append(last)
+            l = x[last]
+            g = np.maximum(f(0), np.maximum((lo - l).astype(f), (l - hi).astype(f))).astype(f)
+            lb = ((g[:, 0] * g[:, 0]).astype(f) + (g[:, 1] * g[:, 1]).astype(f)).astype(f)
+            lb = (lb + (g[:, 2] * g[:, 2]).astype(f)).astype(f)
+            touch = np.nonzero(lb < submax)[0]
+            skipped += len(ids) - len(touch)
+            for r in touch:
+                d3 = (xs[r] - l).astype(f)
+                d = ((d3[:, 0] * d3[:, 0]).astype(f) + (d3[:, 1] * d3[:, 1]).astype(f)).astype(f)
+                d = (d + (d3[:, 2] * d3[:, 2]).astype(f)).astype(f)
+                md[r] = np.minimum(md[r], d)
+                v = np.where(ok[r], md[r], f(-1))
+                submax[r] = v.max()
+                subidx[r] = ids[r][(v == submax[r]) & ok[r]].min()
+            gm = submax.max()
+            last = int(subidx[submax == gm].min())
+        assert np.array_equal(np.array(sel), po.c_fps(x[None], npoint)[0])
+        assert skipped > 0.5 * npoint * len(ids)      # the rule really prunes

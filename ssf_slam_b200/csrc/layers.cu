@@ -216,11 +216,14 @@ __global__ void __launch_bounds__(256) linear_narrow_out_kernel(LinearArgs a) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < K; k0 += 32) {
         const int kn = K - k0 < 32 ? K - k0 : 32;
-#pragma unroll 8
+        float v[32];   // all 32 row pieces of the chunk in flight before the first one is needed
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
             const long long row = r0 + j;
-            sT[warp][j][lane] = (row < a.rows && lane < kn) ? __ldg(a.x1 + (size_t)row * a.ld1 + k0 + lane) : 0.f;
+            v[j] = (row < a.rows && lane < kn) ? __ldg(a.x1 + (size_t)row * a.ld1 + k0 + lane) : 0.f;
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sT[warp][j][lane] = v[j];
         __syncwarp();
         for (int kk = 0; kk < kn; ++kk) {
             const float xv = sT[warp][lane][kk];
@@ -282,7 +285,9 @@ extern "C" int ssf_linear(const float* x1, int c1, int ld1, const float* x2, int
                           const float* add, int ld_add, float clamp2, float* y, int ldy, void* stream) {
     if (rows <= 0 || cout <= 0 || c1 <= 0) return ssf_arg_error("linear: empty input");
     LinearArgs a = {x1, c1, ld1, x2, x2 ? c2 : 0, ld2, Wt, ldw, w_off1, w_off2, bias, rows, cout, act, clamp1, add, ld_add, clamp2, y, ldy};
-    if (x2 == nullptr && cout <= 4 && c1 <= 512 && c1 >= 16) {
+    // (small layers stay on the tiled kernel: one lane per row is a long serial chain when there are too few rows to hide it --
+    // 32768 rows x 256: 57 us here, 17-27 us tiled)
+    if (x2 == nullptr && cout <= 4 && c1 <= 512 && c1 >= 16 && rows > 65536) {
         linear_narrow_out_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
         ssf_count_launch();
         SSF_LAUNCH_CHECK();

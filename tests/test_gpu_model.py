@@ -502,7 +502,8 @@ def test_attention_mix_persistent_kernel(m, P):
     assert torch.equal(a2, Amix) and torch.equal(w2, Awmix)
 
 
-@pytest.mark.parametrize("rows,K,cout", [(5000, 64, 3), (777, 256, 4), (33, 128, 3), (100000, 96, 1), (4099, 3, 32), (1000, 3, 64), (513, 4, 32)])
+@pytest.mark.parametrize("rows,K,cout", [(5000, 64, 3), (777, 256, 4), (33, 128, 3), (100000, 96, 1), (70001, 64, 3), (66000, 256, 4), (65537, 16, 2),
+                                           (4099, 3, 32), (1000, 3, 64), (513, 4, 32)])
 def test_linear_narrow_kernels_equal_the_tiled_kernel(rows, K, cout):
     """Flow heads (cout <= 4) and the first per-point layer (K <= 4) run dedicated kernels (layers.cu linear_narrow_*) with the
     same fmaf chain as the 64 x 64 tiled kernel.  A second, all-zero input block forces the tiled kernel (fmaf(0, w, acc) == acc),

@@ -1,4 +1,4 @@
-"""Developer tool (SSF_CV_TRACE=1 build): per-query visit / insert counts of the Morton-block kNN on realistic clouds."""
+"""Developer tool (SSF_CV_TRACE=1 build): per-query visit / insert counts of the block kNN on realistic clouds."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) knn_warp_scan_kernel(int k, const float* 
 
 
 // ------------------------------------------------------------------ clouds above 16384 points (BASELINE config 5: N = 65536)
-// The Morton sort no longer fits in shared memory, and one lane cannot hold the bounds of all blocks.  So:
+// The curve sort no longer fits in shared memory, and one lane cannot hold the bounds of all blocks.  So:
 //  build : one CTA per cloud, stable LSD radix sort of the (key, index) pairs in global scratch (eight 4-bit passes; thread t
 //          owns a contiguous chunk, per-(digit, thread) counters in shared memory, one block scan per pass -- stable, so equal
 //          keys stay in index order and the layout is the same deterministic function of the cloud as the bitonic build's),
@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(KB_SEARCH_T, 12) knn_blocks_search2_kernel(int
 // Ball query through the same spatial index (either level count): blocks whose box bound exceeds r^2 cannot hold a point in
 // range (the bound is computed with the distance's own rounded operations and is monotone, see the header), every other block
 // is evaluated lane = point.  The reference semantics want the FIRST nsample hits in ascending INDEX order (ASF/SetCover.py:
-// 39-63), while the blocks come in Morton order: the warp keeps the nsample smallest hit indices in a lane-distributed sorted
+// 39-63), while the blocks come in curve order: the warp keeps the nsample smallest hit indices in a lane-distributed sorted
 // list (the kNN list with the index as the key) and counts every hit.  Same output as ssf_ball_query, bit for bit.
 template <bool TWO_LEVEL>
 __global__ void __launch_bounds__(KB_SEARCH_T, 12) ball_query_blocks_kernel(float r2, int nsample, const float* __restrict__ query,

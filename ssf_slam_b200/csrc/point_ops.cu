@@ -86,7 +86,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restrict__ o
 
 // Pruned variant (2048 < N <= 8192), same result bit for bit.  The distance update of an iteration can only lower the running
 // minimum of points that are closer to the new sample than their current minimum, and after the first few dozen samples that is
-// a small neighbourhood.  So the cloud is first sorted along a Morton curve (bitonic sort in shared memory, as the kNN index
+// a small neighbourhood.  So the cloud is first sorted along a Hilbert curve (ssf_cta_sort_u64 in shared memory, as the kNN index
 // build) and kept in shared memory as sorted x / y / z / running-minimum arrays.  32 consecutive sorted points -- a compact
 // blob -- form a "row"; there is one thread per row: sorted row r belongs to warp r % NW (neighbouring rows, which are touched
 // together, go to different warps) as its row j = r / NW, and lane j of that warp keeps the row's bounding box, its largest
@@ -143,7 +143,7 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restr
     float* sx = s_dyn;                                   // [NP] sorted coordinates
     float* sy = sx + NP;
     float* sz = sy + NP;
-    float* smd = sz + NP;                                // [NP] running minima (the Morton keys during the sort)
+    float* smd = sz + NP;                                // [NP] running minima (the curve keys during the sort)
     int* sval = reinterpret_cast<int*>(smd + NP);        // [NP] original index of sorted slot (>= N: padding)
     unsigned long long* skv = reinterpret_cast<unsigned long long*>(smd);   // [NP] key << 32 | index during the sort: smd + sval
     __shared__ unsigned long long s_cand[2][NW];        // per warp: value bits << 32 | index << 13 | slot
@@ -152,7 +152,7 @@ fps_pruned_kernel(const float* __restrict__ xyz, int N, int npoint, int* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* p = xyz + (size_t)blockIdx.x * N * 3;
     int* o = out + (size_t)blockIdx.x * npoint;
-    // cloud bounding box -> 10-bit Morton keys
+    // cloud bounding box -> 10-bit cells, Hilbert keys
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = tid; i < N; i += TS)
 #pragma unroll

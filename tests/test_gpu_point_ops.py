@@ -74,7 +74,7 @@ def test_fps(pu, N, npoint):
 
 @pytest.mark.parametrize("case", ["n2049", "n4097", "all_equal", "planar", "line", "clusters", "select_all", "more_than_all", "lidar", "tiny_far"])
 def test_fps_pruned_kernel_edge_cases(pu, case):
-    """The spatially pruned sampler (2048 < N <= 8192: Morton rows + box bound, point_ops.cu fps_pruned_kernel) must stay
+    """The spatially pruned sampler (2048 < N <= 8192: Hilbert-ordered rows + box bound, point_ops.cu fps_pruned_kernel) must stay
     bit-identical to the plain scan of the oracle where its machinery is stressed: nearly empty padded rows, zero extents,
     massive ties (lowest original index wins), tight clusters far apart, and sampling every point."""
     rng = np.random.default_rng(abs(hash(case)) % 1000)
@@ -107,7 +107,7 @@ def test_fps_pruned_kernel_edge_cases(pu, case):
         npoint = 2048
     else:
         x = (rng.standard_normal((2, 8192, 3)) * 1e-3).astype(np.float32)
-        x[:, 100] += 1e4      # one far outlier squeezes everything else into one Morton cell
+        x[:, 100] += 1e4      # one far outlier squeezes everything else into one cell of the curve
     got = pu.furthest_point_sample(_cuda(x), npoint).cpu().numpy()
     assert np.array_equal(got, po.c_fps(np.ascontiguousarray(x), npoint))
 
@@ -220,7 +220,7 @@ def test_scatter(L, C, n):
                                                (1, 4096, 16385, 16, True, False), (2, 3000, 40000, 16, True, True), (1, 2048, 65536, 7, False, False),
                                                (1, 1024, 100001, 16, True, False), (1, 512, 131072, 3, False, True)])
 def test_knn_blocks_equals_brute_force(B, Nq, Nr, k, dup, off):
-    """The Morton-block search returns exactly the brute-force scan's indices and distances (ties included)."""
+    """The block search returns exactly the brute-force scan's indices and distances (ties included)."""
     import torch
     from ssf_slam_b200 import _native as nat
     g = torch.Generator().manual_seed(Nq + Nr + k)
